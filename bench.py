@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Game-of-Life env step.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (default N=1)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's step on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU (driver does this)
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 4096 envs x 128x128 per GPU, env mode --
+per step and env: toggle_state(action) -> generation -> int8 stability update -> reward
+(/root/reference/CGL/main.py:64-72).  Weak scaling: every rank owns its own 4096 envs (sharding by
+env index, no data-path collective).  A "step" is one launch over all envs of the rank.
+
+Prints ONE JSON line (rank 0).  `value` is in G cell-updates/s over all ranks with state resident in
+HBM; `e2e` is the same metric through the host-buffer C-ABI call (actions H2D + reward D2H per step);
+`roofline` is algorithmic bytes (2.25 B/cell-update) / measured launch time vs the measured HBM peak;
+`cpu_baseline` is the oracle port of the reference's per-cell loop timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "ecen743-project-cgol_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SIDE, ENVS_PER_GPU = 128, 4096
+SPAWN, STABLE = -2, 2                      # CGL/main.py:29, CGL/bench.py:12-13
+BYTES_PER_CELL_ENV = 2.25                  # 1 bit R + 1 bit W + int8 R + int8 W  
+BYTES_PER_CELL_LIFE = 0.25
+L2_BYTES = 126e6
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(kernel):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's per-cell loop (the reference itself is pure Python
+# and cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, budget_s=8.0, threads=None):
+    from oracle import oracle
+    threads = threads or oracle.max_threads()
+    size = SIDE * SIDE
+    # calibrate on a few envs, then size the sample so a step stays <= ~0.4 s
+    n = 4 * threads
+    w = np.stack([oracle.initial_world(SIDE, e) for e in range(n)])
+    s = np.stack([oracle.initial_stable(w[e], SPAWN) for e in range(n)])
+    rs = np.random.RandomState(10 ** 6)
+    t0 = time.perf_counter()
+    oracle.step_batch(w, s, SIDE, rs.randint(size + 1, size=n).astype(np.int32), SPAWN, STABLE, threads)
+    per_env = (time.perf_counter() - t0) / n
+    n_envs = int(max(threads, min(ENVS_PER_GPU, 0.4 / per_env)))
+    max_steps = max(1, int(budget_s / (per_env * n_envs)))
+    steps = min(steps, max_steps)
+    w = np.ascontiguousarray(np.resize(w, (n_envs, size)))
+    s = np.ascontiguousarray(np.resize(s, (n_envs, size)))
+    acts = rs.randint(size + 1, size=(warmup + steps, n_envs)).astype(np.int32)
+    for i in range(warmup):
+        oracle.step_batch(w, s, SIDE, acts[i], SPAWN, STABLE, threads)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle.step_batch(w, s, SIDE, acts[warmup + i], SPAWN, STABLE, threads)
+    dt = time.perf_counter() - t0
+    gcups = n_envs * size * steps / dt / 1e9
+    return {"value": gcups, "unit": "Gcell-updates/s", "cores": threads, "kind": "port",
+            "sample": f"{n_envs} envs x {SIDE}x{SIDE} x {steps} steps (toggle+step+reward), oracle/cgl_oracle.c "
+                      f"= C port of CGL/CGL.py:211-243, {threads} host threads",
+            "env_steps_per_s": n_envs * steps / dt, "ms_per_step": dt / steps * 1e3, "steps": steps}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_arm(args.steps, min(args.warmup, 2), budget_s=20.0)
+    line = {"impl": "reference", "metric": "life_cell_updates_per_s", "value": base["value"], "unit": base["unit"],
+            "n_gpus": args.gpus, "steps": base["steps"], "warmup": min(args.warmup, 2),
+            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": workload_config(args.gpus, None),
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "env_steps_per_s": base["env_steps_per_s"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, replicas):
+    return {"workload": f"C2: {ENVS_PER_GPU} envs x {SIDE}x{SIDE} per GPU, env mode (toggle + generation + int8 "
+                        f"stability + reward), spawn {SPAWN} / stable {STABLE}",
+            "envs_per_gpu": ENVS_PER_GPU, "side": SIDE, "total_envs": ENVS_PER_GPU * n_gpus,
+            "parallelism": f"env-index sharding x{n_gpus}, no data-path collective",
+            "l2": None if replicas is None else
+            f"inputs larger than L2: {replicas} rotating replicas of the env batch "
+            f"({replicas * ENVS_PER_GPU * SIDE * SIDE * 1.25 / 2**20:.0f} MiB touched round-robin > 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def time_steps(torch, fn, steps, barrier):
+    """K calls of fn(i) bracketed by barrier + synchronize, CUDA events on the launching stream."""
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=4, help="rotating env batches (working set > L2)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3/C4/C5 side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from cgl_b200 import native
+    from cgl_b200.batched import BatchedSim
+    native.load()                                           # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    size = SIDE * SIDE
+    B, R, K, W = ENVS_PER_GPU, max(1, args.replicas), args.steps, args.warmup
+    sims = [BatchedSim(B, SIDE, seed=rank * 10 ** 5 + r * B, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE,
+                       device=dev, rng="device") for r in range(R)]
+    n_act = 16
+    g = torch.Generator(device=dev); g.manual_seed(10 ** 6 + rank)
+    actions = torch.randint(0, size + 1, (n_act, B), dtype=torch.int32, device=dev, generator=g)
+
+    def step(i):
+        sims[i % R].step(actions[i % n_act])
+
+    for i in range(W):
+        step(i)
+    launches0 = sum(s.launches for s in sims)
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    dt = max_over_ranks(time_steps(torch, step, K, barrier))
+    clocks = sampler.stop() if sampler else None
+    gpu_launches = sum(s.launches for s in sims) - launches0
+    cells_per_step = B * size * world
+    value = cells_per_step * K / dt / 1e9
+    ms_per_step = dt / K * 1e3
+
+    # L2-resident variant (one replica, 80 MiB working set inside the 126 MB L2) -- reported, not the headline
+    dt_l2 = max_over_ranks(time_steps(torch, lambda i: sims[0].step(actions[i % n_act]), K, barrier))
+
+    # ---- end to end through the host-buffer C-ABI call (actions H2D, reward D2H every step) ----
+    e2e = None
+    if not args.no_e2e:
+        acts_h = [torch.randint(0, size + 1, (B,), dtype=torch.int32).pin_memory() for _ in range(4)]
+        rew_h = torch.empty(B, dtype=torch.int32).pin_memory()
+        ke = max(10, min(K, 100))
+        for i in range(3):
+            sims[i % R].step_host(acts_h[i % 4], rew_h)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            sims[i % R].step_host(acts_h[i % 4], rew_h)     # returns after the D2H copy completed
+        torch.cuda.synchronize()
+        dte = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        obs_h = torch.empty((B, size), dtype=torch.int8).pin_memory()
+        ko = 5
+        sims[0].step_host(acts_h[0], rew_h, obs_h)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for i in range(ko):
+            sims[i % R].step_host(acts_h[i % 4], rew_h, obs_h)
+        torch.cuda.synchronize()
+        dto = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": cells_per_step * ke / dte / 1e9, "unit": "Gcell-updates/s",
+               "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B, "steps": ke,
+               "api": "BatchedSim.step_host -> cgl_env_step_host (pinned actions H2D, step, reward D2H, sync); "
+                      "the observation stays device-resident for the GPU Q-network",
+               "env_steps_per_s": B * world * ke / dte,
+               "with_obs_to_host": {"value": cells_per_step * ko / dto / 1e9, "unit": "Gcell-updates/s",
+                                    "d2h_bytes_per_step": 4 * B + B * size, "steps": ko}}
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = BYTES_PER_CELL_ENV * B * size / (dt / K) / 1e9          # per GPU, per launch
+    kernel = f"env_step_fused_kernel<{SIDE}>"
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": recorded_traffic(kernel), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_CELL_ENV * B * size,
+                "avg_launch_ms": dt / K * 1e3, "l2_resident_variant_gbs": BYTES_PER_CELL_ENV * B * size / (dt_l2 / K) / 1e9}
+
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras = run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak)
+        except Exception as exc:  # noqa: BLE001
+            extras = {"error": repr(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_arm(steps=10 ** 6, warmup=1, budget_s=8.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "life_cell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, R),
+                "env_steps_per_s": B * world * K / dt, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "l2_resident_value": cells_per_step * K / dt_l2 / 1e9,
+                "extras": extras}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
+    """Side measurements of the other BASELINE configs (short; not the headline line)."""
+    from cgl_b200 import native
+    from cgl_b200.batched import BatchedSim
+    lib = native.load()
+    out = {}
+    # C3: 65536 envs x 64x64, sharded by env index over the ranks (strong scaling over N)
+    side, total = 64, 65536
+    sim = BatchedSim.shard(total, side, rank, world, seed=0, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE,
+                           device=dev, rng="device")
+    acts = torch.randint(0, side * side + 1, (8, sim.n_envs), dtype=torch.int32, device=dev)
+    for i in range(5):
+        sim.step(acts[i % 8])
+    k = 50
+    dt = max_over_ranks(time_steps(torch, lambda i: sim.step(acts[i % 8]), k, barrier))
+    out["c3_envs65536_side64"] = {"gcups": total * side * side * k / dt / 1e9, "env_steps_per_s": total * k / dt,
+                                  "ms_per_step": dt / k * 1e3, "scaling": "strong",
+                                  "hbm_frac": BYTES_PER_CELL_ENV * sim.n_envs * side * side / (dt / k) / 1e9 / peak,
+                                  "working_set_mib_per_gpu": sim.n_envs * side * side * 1.25 / 2 ** 20}
+    del sim, acts
+    torch.cuda.empty_cache()
+    if world == 1:
+        # C4 / C5: single large grids, life mode, one GPU (row-band multi-GPU runs: see bench_bands.py)
+        for name, n in (("c4_life_65536", 65536), ("c5_life_32768", 32768)):
+            words = n * (n // 32)
+            a = torch.randint(-2 ** 31, 2 ** 31 - 1, (words,), dtype=torch.int32, device=dev)
+            b = torch.empty_like(a)
+            st = native.current_stream()
+            bufs = [a, b]
+
+            def gen(i):
+                native.check(lib.cgl_life_step(native.dptr(bufs[i & 1]), native.dptr(bufs[(i + 1) & 1]), 1, n, n, 1,
+                                               None, st))
+            for i in range(4):
+                gen(i)
+            k = 40
+            dt = time_steps(torch, gen, k, barrier)
+            out[name] = {"gcups": n * n * k / dt / 1e9, "ms_per_gen": dt / k * 1e3, "k": 1,
+                         "hbm_frac": BYTES_PER_CELL_LIFE * n * n / (dt / k) / 1e9 / peak}
+            del a, b, bufs
+            torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,335 @@
+"""CGL -- drop-in replacement for the reference's `CGL.py` module, B200-native.
+
+Usage is the reference's own (/root/reference/CGL/main.py:1,29; bench.py:5,38): put this
+directory on sys.path (or run the script from it) and
+
+    import CGL
+    env = CGL.sim(side=10, seed=0, gpu=True, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    env.toggle_state(action); env.step(); obs = env.get_stable(vector=True, shallow=True); r = env.reward()
+
+Same constructor keywords, same methods, same exception classes as `class sim`
+(/root/reference/CGL/CGL.py:53-354); every method below cites the lines it mirrors.  What
+changed is everything underneath: the state lives ON THE DEVICE (bit-packed world + int8
+stability) and is stepped by libcgl_b200.so; numpy arrays are materialised at
+the API boundary only.  There is no CPU path: `gpu=False` / `step(forceCPU=True)` raise, and a
+missing CUDA library raises `cgl_b200.native.CglNativeError` at construction.
+
+Deliberate deviations (all documented in DESIGN.md section 2):
+  * cells must be 0/1 and the grid square (the reference lets other uint8 values and
+    non-square sizes flow into its arithmetic unchecked) -> ValueError here;
+  * shallow views are pinned host mirrors kept up to date by every state-changing call
+    (reads see live state, aliasing `state is n_state` holds, CGL/main.py:60,70); writes INTO a
+    shallow view do not reach the device -- use toggle_state / update_state / load.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+# Same environment switch as the reference (CGL/CGL.py:33-42).
+if "GPU_CAPABLE" in os.environ:
+    GPU_CAPABLE = os.environ["GPU_CAPABLE"].lower()
+    if GPU_CAPABLE == "true":
+        GPU_CAPABLE = True
+    elif GPU_CAPABLE == "false":
+        GPU_CAPABLE = False
+    else:
+        raise TypeError('GPU_CAPABLE must either be "TRUE" or "FALSE"!')
+else:
+    GPU_CAPABLE = True
+
+_QUIET = os.environ.get("CGL_QUIET", "0") not in ("0", "", "false")
+
+
+def _say(*a):
+    if not _QUIET:
+        print(*a)
+
+
+def _check_int8(name, v):
+    if not -128 <= v <= 127:
+        # numpy 2 raises OverflowError at `stable[...] = spawn` (CGL/CGL.py:112)
+        raise OverflowError(f"Python integer {v} out of bounds for int8 ({name})")
+
+
+class sim:
+    """Conway's Game of Life environment with a per-cell int8 stability counter.
+
+    Constructor arguments as in the reference (CGL/CGL.py:55): `state` (1-D/2-D ndarray of 0/1)
+    or `side`+`seed` for the reference's random start; `gpu` must be True (and equal the
+    GPU_CAPABLE environment switch); `gpu_select` is the CUDA device index; `warp` is accepted and
+    validated for compatibility (launch geometry is chosen by the library)."""
+
+    def __init__(self, state=None, side=8, seed=8, gpu=False, gpu_select=0, warp=8,
+                 spawnStabilityFactor=-1, stableStabilityFactor=1):
+        # ---- validation: same order and exception classes as CGL/CGL.py:57-82 -------------
+        if not isinstance(state, np.ndarray) and state is not None and not isinstance(state, list):
+            raise TypeError("state variable must be a list or Numpy ndarray!")
+        if not isinstance(side, int):
+            raise TypeError("side must be integer!")
+        if side < 1:
+            raise ValueError("side must be positive integer greater than 0!")
+        if not isinstance(seed, int):
+            raise TypeError("seed must be integer!")
+        if seed < 0:
+            raise ValueError("seed must be positive integer!")
+        if not isinstance(gpu, bool):
+            raise TypeError("gpu must be bool!")
+        if not isinstance(warp, int):
+            raise TypeError("warp must be integer!")
+        if warp < 0:
+            raise ValueError("warp must be positive integer!")
+        if not isinstance(spawnStabilityFactor, int):
+            raise TypeError("spawnStabilityFactor must be an integer!")
+        if not isinstance(stableStabilityFactor, int):
+            raise TypeError("stableStabilityFactor must be an integer!")
+        if GPU_CAPABLE != gpu:
+            raise TypeError(f'the os enviornment variable "GPU_CAPABLE" (defaults to true) is {GPU_CAPABLE} and '
+                            f'"gpu" is {gpu}. Both must be equal in value!\n'
+                            'To launch use: GPU_CAPABLE="true\\false" python3 <script.py>')
+        if not gpu:
+            raise RuntimeError("this build of CGL is GPU-only (B200-native, no CPU step): construct with gpu=True "
+                               "and GPU_CAPABLE=true, or import the reference CGL.py for its CPU loop")
+
+        self.count = 0
+        self.seed = seed
+        self.spawnStabilityFactor = spawnStabilityFactor
+        self.stableStabilityFactor = stableStabilityFactor
+        self.gpu = gpu
+
+        if state is not None:
+            state = state.flatten().astype(np.uint8)       # lists fail here like the reference (:94, N4)
+            if state.size == 0:
+                raise ValueError("state must be size greater than 0!")
+            world0 = self._validated_cells(state)
+            self.size = world0.size
+            self.side = int(np.sqrt(self.size))
+            if self.side * self.side != self.size:
+                raise ValueError(f"state must be square: got {self.size} cells")
+        else:
+            self.side = side
+            self.size = side ** 2
+            world0 = None
+        _check_int8("spawnStabilityFactor", spawnStabilityFactor)
+        _check_int8("stableStabilityFactor", stableStabilityFactor)
+
+        # ---- device setup (replaces CGL/CGL.py:116-195) ------------------------------------
+        import torch
+        from cgl_b200 import native
+        from cgl_b200.batched import BatchedSim
+        self._torch = torch
+        native.load()                                       # fail loudly before touching the device
+        if not torch.cuda.is_available():
+            raise native.CglNativeError("no CUDA device visible: CGL.sim(gpu=True) needs a GPU (no CPU fallback)")
+        n_dev = torch.cuda.device_count()
+        if not isinstance(gpu_select, int) or gpu_select < 0 or gpu_select > n_dev - 1:
+            raise ValueError(f"gpu_select={gpu_select}, however the device which can be chosen are: {range(n_dev)}.")
+        prop = torch.cuda.get_device_properties(gpu_select)
+        _say("Number of devices detected:", n_dev)
+        _say("Device selected:", gpu_select)
+        _say("\tName:", prop.name)
+        _say("\tCompute capability:", (prop.major, prop.minor))
+        _say("\tTotal memory:", prop.total_memory / 1048576, "MB")
+        _say("\tSMs:", prop.multi_processor_count)
+        self._dev = torch.device("cuda", gpu_select)
+        self._b = BatchedSim(1, self.side, seed=seed, spawnStabilityFactor=spawnStabilityFactor,
+                             stableStabilityFactor=stableStabilityFactor, device=self._dev,
+                             states=None if world0 is None else world0[None, :])
+        self._alloc_mirrors()
+        _say("CGL is now running...")
+
+    # ------------------------------------------------------------------------------ internals
+    @staticmethod
+    def _validated_cells(flat_u8: np.ndarray) -> np.ndarray:
+        if flat_u8.size and flat_u8.max() > 1:
+            raise ValueError("cells must be 0 or 1 (bit-packed device state); got values > 1")
+        return np.ascontiguousarray(flat_u8)
+
+    def _alloc_mirrors(self):
+        torch = self._torch
+        self._m_world_t = torch.empty(self.size, dtype=torch.uint8).pin_memory()
+        self._m_stable_t = torch.empty(self.size, dtype=torch.int8).pin_memory()
+        self._m_world = self._m_world_t.numpy()
+        self._m_stable = self._m_stable_t.numpy()
+        self._world_fresh = self._stable_fresh = False
+        self._world_live = self._stable_live = False       # a shallow view has been handed out
+
+    def _changed(self, world=True, stable=True):
+        """Device state changed: invalidate mirrors, eagerly refresh the ones with live views."""
+        if world:
+            self._world_fresh = False
+            if self._world_live:
+                self._sync_world()
+        if stable:
+            self._stable_fresh = False
+            if self._stable_live:
+                self._sync_stable()
+
+    def _sync_world(self):
+        if not self._world_fresh:
+            self._m_world_t.copy_(self._b.get_state().view(-1))
+            self._world_fresh = True
+        return self._m_world
+
+    def _sync_stable(self):
+        if not self._stable_fresh:
+            self._m_stable_t.copy_(self._b.stable.view(-1))
+            self._stable_fresh = True
+        return self._m_stable
+
+    # reference attribute names (read access): live host views of the device state
+    @property
+    def world(self):
+        self._world_live = True
+        return self._sync_world()
+
+    @property
+    def stable(self):
+        self._stable_live = True
+        return self._sync_stable()
+
+    @property
+    def initState(self):
+        torch = self._torch
+        from cgl_b200 import native
+        out = torch.empty((1, self.size), dtype=torch.uint8, device=self._dev)
+        native.check(self._b._lib.cgl_unpack(native.dptr(self._b._init_world), native.dptr(out), 1, self.side,
+                                             self.side, self._b._stream()), "cgl_unpack")
+        return out.cpu().numpy().reshape(-1)
+
+    @property
+    def initStable(self):
+        return self._b._init_stable.cpu().numpy().reshape(-1)
+
+    # ------------------------------------------------------------------------------ simulator
+    def step(self, forceCPU=False):
+        """One generation + stability update (CGL/CGL.py:247-252; kernel :147-181)."""
+        if forceCPU:
+            raise RuntimeError("forceCPU is not available in the B200 build (no CPU step); use the reference for that")
+        self.count += 1
+        self._b.step(None)
+        self._changed()
+
+    def reward(self):
+        """np.int32 sum of the stability vector (CGL/CGL.py:255-256)."""
+        return np.int32(self._b.reward().item())
+
+    def alive(self):
+        """np.uint32 number of live cells (CGL/CGL.py:259-260)."""
+        return np.uint32(self._b.alive().item())
+
+    def reset(self):
+        """Back to the initial state; `count` is not reset (CGL/CGL.py:264-266)."""
+        self._b.reset()
+        self._changed()
+
+    def match(self, terminalState):
+        """(world == terminalState.flatten()).all()  (CGL/CGL.py:269-270)."""
+        flat = np.asarray(terminalState).flatten()
+        if flat.size != self.size:
+            raise ValueError(f"terminalState has {flat.size} cells, expected {self.size}")
+        if flat.size and (flat.min() < 0 or flat.max() > 1 or np.any(flat != flat.astype(np.uint8))):
+            return False                                    # the world is binary: cannot be equal
+        return self._b.match(self._torch.from_numpy(np.ascontiguousarray(flat.astype(np.uint8)))[None, :])
+
+    # ------------------------------------------------------------------------------ I/O
+    def get_state(self, vector=False, shallow=False):
+        """World as uint8 vector or (side, side) matrix (CGL/CGL.py:274-278)."""
+        if shallow:
+            self._world_live = True
+        w = self._sync_world()
+        out = w if vector else w.reshape((self.side, self.side))
+        return out if shallow else np.copy(out)
+
+    def get_stable(self, vector=False, shallow=False):
+        """Stability (the observation) as int8 vector or matrix (CGL/CGL.py:281-285)."""
+        if shallow:
+            self._stable_live = True
+        s = self._sync_stable()
+        out = s if vector else s.reshape((self.side, self.side))
+        return out if shallow else np.copy(out)
+
+    def get_side(self):
+        return self.side
+
+    def get_count(self):
+        return self.count
+
+    def get_seed(self):
+        return self.seed
+
+    def get_state_dim(self):
+        return self.size
+
+    def get_state_space_dim(self):
+        return 2 ** self.size
+
+    def get_action_space_dim(self):
+        return self.size + 1        # the last action is "do nothing" (CGL/CGL.py:308-309)
+
+    def update_state(self, newState, side):
+        """Replace the world, keep the stability plane (CGL/CGL.py:312-317)."""
+        temp = newState.flatten().astype(np.uint8)
+        if temp.size != self.size or self.side != side:
+            raise ValueError("The new state must have the same size and side as the original state!\n"
+                             f"Was given size={temp.size} and side={side} but was expecting size={self.size} and side={self.side}.")
+        cells = self._validated_cells(temp)
+        self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
+        self._changed(world=True, stable=False)
+
+    def toggle_state(self, indx):
+        """Toggle the listed cells and set their stability to spawn (CGL/CGL.py:322-328).
+        Duplicates toggle once; the scalar `size` is the silent "do nothing"; anything else out of
+        range raises ValueError."""
+        indx = np.array(indx)
+        if np.all(indx < self.size) and np.all(indx >= 0):
+            if indx.dtype.kind not in "iu":
+                raise IndexError("arrays used as indices must be of integer (or boolean) type")
+            flat = np.ascontiguousarray(indx.reshape(-1), dtype=np.int32)
+            if flat.size:
+                self._b.toggle(self._torch.from_numpy(flat).to(self._dev)[None, :])
+                self._changed()
+        elif indx != self.size:     # an array with >1 element raises ValueError here, like the reference
+            raise ValueError("Not all indexes are valid!\nIndexes must be positive and less than the size of the "
+                             f"state {self.size}.")
+
+    def save(self):
+        """(world, stable, side, count, spawn, stable_max) -- host copies (CGL/CGL.py:332-333)."""
+        return (np.copy(self._sync_world()), np.copy(self._sync_stable()), self.side, self.count,
+                self.spawnStabilityFactor, self.stableStabilityFactor)
+
+    def load(self, newState, newstable, side, count, spawnStabilityFactor, stableStabilityFactor):
+        """Restore an exact setup (CGL/CGL.py:336-354); device buffers are re-created if `side` changed."""
+        if not isinstance(newState, np.ndarray) or not isinstance(newstable, np.ndarray):
+            raise TypeError("newState and newstable variables must be a Numpy ndarray!")
+        if not isinstance(side, int) or not isinstance(count, int):
+            raise TypeError("side and count must be integer!")
+        if side < 1 or count < 0:
+            raise ValueError("side and count must be positive integers and side greater than 0!")
+        if not isinstance(spawnStabilityFactor, int):
+            raise TypeError("spawnStabilityFactor must be an integer!")
+        if not isinstance(stableStabilityFactor, int):
+            raise TypeError("stableStabilityFactor must be an integer!")
+        _check_int8("spawnStabilityFactor", spawnStabilityFactor)
+        _check_int8("stableStabilityFactor", stableStabilityFactor)
+        cells = self._validated_cells(newState.flatten().astype(np.uint8))
+        stab = np.ascontiguousarray(newstable.flatten().astype(np.int8))
+        if cells.size != side * side or stab.size != side * side:
+            raise ValueError(f"newState/newstable must have side*side = {side * side} cells")
+        from cgl_b200.batched import BatchedSim
+        self.stableStabilityFactor = stableStabilityFactor
+        self.spawnStabilityFactor = spawnStabilityFactor
+        resized = side != self.side
+        self.size = side ** 2
+        self.side = side
+        self.count = count
+        if resized:
+            self._b = BatchedSim(1, side, seed=self.seed, spawnStabilityFactor=spawnStabilityFactor,
+                                 stableStabilityFactor=stableStabilityFactor, device=self._dev, states=cells[None, :])
+            self._alloc_mirrors()
+        else:
+            self._b.spawn, self._b.stable_max = spawnStabilityFactor, stableStabilityFactor
+            self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
+        self._b.stable.copy_(self._torch.from_numpy(stab)[None, :])
+        self._changed()

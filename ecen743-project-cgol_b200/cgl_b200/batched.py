@@ -1,0 +1,237 @@
+"""BatchedSim -- B independent Game-of-Life environments resident on one B200.
+
+Device layout:
+  world   uint32 [B, side, W]   1 bit per cell, W = ceil(side/32), two ping-pong planes
+  stable  int8   [B, side*side] the reference's row-major stability vector == the observation
+All stepping goes through libcgl_b200.so (`cgl_env_step`); torch only owns memory and streams.
+
+Semantics per env are those of the reference's `sim` (/root/reference/CGL/CGL.py):
+toggle_state (:322-328) -> step (:247-252, kernel :147-181) -> reward (:255-256) / get_stable
+(:281-285), i.e. the body of the DQN loop CGL/main.py:64-72, for all envs in one launch.
+
+Sharding by env index (multi-GPU, no communication): `BatchedSim.shard(...)` gives rank r the
+envs [r*B/G, (r+1)*B/G); env e is always seeded `seed + e` with its GLOBAL index, so results
+do not depend on the number of GPUs.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import native
+
+
+def reference_initial_world(side: int, seed: int) -> np.ndarray:
+    """The reference's random start: CGL/CGL.py:104-107 (legacy MT19937 `np.random.seed`)."""
+    return np.random.RandomState(seed).randint(2, size=side * side, dtype=np.uint8)
+
+
+class BatchedSim:
+    def __init__(self, n_envs: int, side: int, seed: int = 0, spawnStabilityFactor: int = -1,
+                 stableStabilityFactor: int = 1, device="cuda", states=None, first_env: int = 0,
+                 rng: str = "reference", max_steps: int | None = None):
+        if not isinstance(n_envs, int) or n_envs < 1:
+            raise ValueError("n_envs must be a positive integer")
+        if not isinstance(side, int) or side < 1:
+            raise ValueError("side must be positive integer greater than 0!")
+        for name, v in (("spawnStabilityFactor", spawnStabilityFactor), ("stableStabilityFactor", stableStabilityFactor)):
+            if not isinstance(v, int):
+                raise TypeError(f"{name} must be an integer!")
+            if not -128 <= v <= 127:
+                raise OverflowError(f"{name}={v} out of bounds for int8")
+        self._lib = native.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise native.CglNativeError("BatchedSim needs a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_envs, self.side, self.size = n_envs, side, side * side
+        self.W = (side + 31) // 32
+        self.seed, self.first_env = seed, first_env
+        self.spawn, self.stable_max = spawnStabilityFactor, stableStabilityFactor
+        self.count = 0
+        self.max_steps = max_steps
+        self.fused = bool(self._lib.cgl_env_step_is_fused(side))
+        self.launches = 0                                   # kernels launched so far (bench evidence)
+
+        with torch.cuda.device(self.device):
+            B, size, W = n_envs, self.size, self.W
+            self._wa = torch.zeros((B, side, W), dtype=torch.int32, device=self.device)
+            self._wb = torch.zeros_like(self._wa)
+            self.stable = torch.zeros((B, size), dtype=torch.int8, device=self.device)
+            self._reward = torch.zeros(B, dtype=torch.int32, device=self.device)
+            self._alive = torch.zeros(B, dtype=torch.int32, device=self.device)   # uint32 bits
+            self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._done = {False: torch.zeros(B, dtype=torch.bool, device=self.device),
+                          True: torch.ones(B, dtype=torch.bool, device=self.device)}
+            if states is not None:
+                cells = torch.as_tensor(np.ascontiguousarray(states, dtype=np.uint8).reshape(B, size))
+                self.set_state(cells.to(self.device))
+            elif rng == "reference":
+                host = np.empty((B, size), np.uint8)
+                for e in range(B):
+                    host[e] = reference_initial_world(side, seed + first_env + e)
+                self.set_state(torch.from_numpy(host).to(self.device))
+            elif rng == "device":
+                # synthetic Bernoulli(0.5) cells drawn on the device (bench-only: not the reference RNG)
+                g = torch.Generator(device=self.device)
+                g.manual_seed(seed + first_env)
+                cells = torch.randint(0, 2, (B, size), dtype=torch.uint8, device=self.device, generator=g)
+                self.set_state(cells)
+            else:
+                raise ValueError("rng must be 'reference' or 'device'")
+            self.init_stable()
+            self._init_world = self._wa.clone()
+            self._init_stable = self.stable.clone()
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def shard(cls, total_envs: int, side: int, rank: int, world_size: int, **kw) -> "BatchedSim":
+        """Rank `rank` of `world_size` owns envs [rank*B/G, (rank+1)*B/G) -- no data-path collective."""
+        if total_envs % world_size:
+            raise ValueError("total_envs must be divisible by world_size")
+        per = total_envs // world_size
+        return cls(per, side, first_env=rank * per, **kw)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def world(self) -> torch.Tensor:
+        """Current packed world plane, int32-typed storage of uint32 words [B, side, W]."""
+        return self._wa
+
+    def set_state(self, cells: torch.Tensor) -> None:
+        """cells: uint8 [B, size] on the device (nonzero = alive) -> packed current world."""
+        assert cells.dtype == torch.uint8 and cells.is_cuda and cells.numel() == self.n_envs * self.size
+        cells = cells.contiguous()
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_pack(native.dptr(cells), native.dptr(self._wa), self.n_envs,
+                                            self.side, self.side, self._stream()), "cgl_pack")
+        self.launches += 1
+
+    def init_stable(self) -> None:
+        """stable = alive ? spawn : 0 (CGL/CGL.py:111-112)."""
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_init_stable(native.dptr(self._wa), native.dptr(self.stable),
+                                                   self.n_envs, self.side, self.spawn, self._stream()),
+                         "cgl_init_stable")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ env API
+    def reset(self) -> torch.Tensor:
+        """All envs back to their initial world/stability (CGL/CGL.py:264-266; count untouched)."""
+        self._wa.copy_(self._init_world)
+        self.stable.copy_(self._init_stable)
+        return self.stable
+
+    def step(self, actions: torch.Tensor | None = None, want_alive: bool = False):
+        """One env step for every env.  actions: int32 [B] on the device (or None = plain step,
+        CGL/bench.py:39-40); action == side*side is the reference's "do nothing".
+        Returns (obs, reward, done): obs = the live int8 [B, size] stability tensor, reward =
+        int32 [B] (overwritten by the next step), done = bool [B] (count >= max_steps; the
+        reference has no terminal state, CGL/main.py:63)."""
+        if actions is not None:
+            if actions.dtype != torch.int32 or not actions.is_cuda or actions.numel() != self.n_envs:
+                raise TypeError("actions must be an int32 CUDA tensor with one entry per env")
+            actions = actions.contiguous()
+        with torch.cuda.device(self.device):
+            rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                        self.n_envs, self.side, native.dptr(actions), self.spawn,
+                                        self.stable_max, native.dptr(self._reward),
+                                        native.dptr(self._alive) if want_alive else None,
+                                        native.dptr(self._err), self._stream())
+        native.check(rc, "cgl_env_step")
+        self._wa, self._wb = self._wb, self._wa
+        self.count += 1
+        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions is not None))
+        done = self._done[self.max_steps is not None and self.count >= self.max_steps]
+        return self.stable, self._reward, done
+
+    def check_actions(self) -> None:
+        """Synchronise and raise ValueError if any action since the last check was outside
+        [0, size] (the reference raises at toggle time, CGL/CGL.py:327-328)."""
+        if int(self._err.item()) != 0:
+            self._err.zero_()
+            raise ValueError(f"Not all indexes are valid!\nIndexes must be positive and less than the size of the state {self.size}.")
+
+    def toggle(self, idx: torch.Tensor) -> None:
+        """toggle_state for every env: idx int32 [B, K] (K indices per env; duplicates toggle once;
+        `size` = no-op).  CGL/CGL.py:322-328, CGL_action+/helper.py:108-132 (K = 4)."""
+        if idx.dtype != torch.int32 or not idx.is_cuda:
+            raise TypeError("idx must be an int32 CUDA tensor")
+        idx = idx.reshape(self.n_envs, -1).contiguous()
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_toggle(native.dptr(self._wa), native.dptr(self.stable), self.n_envs,
+                                              self.side, native.dptr(idx), idx.shape[1], self.spawn,
+                                              native.dptr(self._err), self._stream()), "cgl_toggle")
+        self.launches += 1
+
+    def reward(self) -> torch.Tensor:
+        """int32 [B] = sum of each env's stability vector (CGL/CGL.py:255-256)."""
+        out = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_reward(native.dptr(self.stable), self.n_envs, self.size,
+                                              native.dptr(out), self._stream()), "cgl_reward")
+        self.launches += 1
+        return out
+
+    def alive(self) -> torch.Tensor:
+        """int64 [B] live-cell counts (CGL/CGL.py:259-260)."""
+        out = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_alive(native.dptr(self._wa), self.n_envs, self.side * self.W,
+                                             native.dptr(out), self._stream()), "cgl_alive")
+        self.launches += 1
+        return out.to(torch.int64) & 0xFFFFFFFF
+
+    def last_alive(self) -> torch.Tensor:
+        """Live-cell counts written by the last step(want_alive=True)."""
+        return self._alive.to(torch.int64) & 0xFFFFFFFF
+
+    def get_state(self) -> torch.Tensor:
+        """uint8 [B, size] cells in the reference's array format (unpacked copy)."""
+        out = torch.empty((self.n_envs, self.size), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_unpack(native.dptr(self._wa), native.dptr(out), self.n_envs,
+                                              self.side, self.side, self._stream()), "cgl_unpack")
+        self.launches += 1
+        return out
+
+    def get_stable(self) -> torch.Tensor:
+        """int8 [B, size]: the live observation tensor (shallow, like get_stable(shallow=True))."""
+        return self.stable
+
+    def match(self, other_cells: torch.Tensor) -> bool:
+        """(world == other).all() over the whole batch (CGL/CGL.py:269-270); other: uint8 [B, size]."""
+        tmp = torch.empty_like(self._wb)
+        eq = torch.empty(1, dtype=torch.int32, device=self.device)
+        other_cells = other_cells.to(self.device, torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_pack(native.dptr(other_cells), native.dptr(tmp), self.n_envs,
+                                            self.side, self.side, self._stream()), "cgl_pack")
+            native.check(self._lib.cgl_match(native.dptr(self._wa), native.dptr(tmp), self._wa.numel(),
+                                             native.dptr(eq), self._stream()), "cgl_match")
+        self.launches += 3
+        return bool(eq.item())
+
+    # ------------------------------------------------------------------ host-buffer step (e2e)
+    def step_host(self, actions_host: torch.Tensor | None, reward_host: torch.Tensor,
+                  obs_host: torch.Tensor | None = None) -> None:
+        """The same step driven from HOST buffers: actions int32 [B] (pinned) are copied H2D, the
+        step runs, reward int32 [B] (and the int8 observation if obs_host is given) come back D2H;
+        returns after the copies completed.  One C-ABI call: cgl_env_step_host."""
+        if not hasattr(self, "_act_dev"):
+            self._act_dev = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.cgl_env_step_host(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                             self.n_envs, self.side, native.dptr(actions_host),
+                                             native.dptr(self._act_dev), self.spawn, self.stable_max,
+                                             native.dptr(self._reward), native.dptr(reward_host),
+                                             native.dptr(obs_host), self._stream())
+        native.check(rc, "cgl_env_step_host")
+        self._wa, self._wb = self._wb, self._wa
+        self.count += 1
+        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_host is not None))

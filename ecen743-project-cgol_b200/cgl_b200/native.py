@@ -1,0 +1,101 @@
+"""ctypes binding of libcgl_b200.so (the C ABI declared in include/cgl_b200.h).
+
+PyTorch is used by the callers for device memory and streams only; no torch type crosses this
+boundary -- every call passes raw device pointers, sizes and a cudaStream_t.
+
+There is NO CPU fallback: if the CUDA library cannot be loaded (or built), importing the
+product fails loudly with `CglNativeError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, "libcgl_b200.so")
+
+E_BADARG, E_BADINDEX, E_NOMEM = -1, -2, -3
+
+
+class CglNativeError(RuntimeError):
+    """Raised when libcgl_b200.so is missing or one of its entry points reports an error."""
+
+
+_vp, _u64, _u32, _i = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/cgl_b200.h one to one
+SIGNATURES = {
+    "cgl_abi_version": (_i, []),
+    "cgl_last_error": (ctypes.c_char_p, []),
+    "cgl_device_count": (_i, [ctypes.POINTER(_i)]),
+    "cgl_device_info": (_i, [_i, ctypes.c_char_p, _i, ctypes.POINTER(_i), ctypes.POINTER(_i),
+                             ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
+    "cgl_words_per_row": (_u32, [_u32]),
+    "cgl_pack": (_i, [_vp, _vp, _u64, _u32, _u32, _vp]),
+    "cgl_unpack": (_i, [_vp, _vp, _u64, _u32, _u32, _vp]),
+    "cgl_init_stable": (_i, [_vp, _vp, _u64, _u32, _i, _vp]),
+    "cgl_toggle": (_i, [_vp, _vp, _u64, _u32, _vp, _u32, _i, _vp, _vp]),
+    "cgl_env_step": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "cgl_env_step_is_fused": (_i, [_u32]),
+    "cgl_env_step_launches": (_i, [_u32, _i]),
+    "cgl_life_step": (_i, [_vp, _vp, _u64, _u32, _u32, _i, _vp, _vp]),
+    "cgl_life_run": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _u32, ctypes.POINTER(_i), _vp]),
+    "cgl_reward": (_i, [_vp, _u64, _u64, _vp, _vp]),
+    "cgl_alive": (_i, [_vp, _u64, _u64, _vp, _vp]),
+    "cgl_match": (_i, [_vp, _vp, _u64, _vp, _vp]),
+    "cgl_step_state_gpu": (_i, [_vp, _vp, _u32, _i, _i]),
+    "cgl_env_step_host": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "cgl_ipc_get_handle": (_i, [_vp, _vp]),
+    "cgl_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "cgl_ipc_close_handle": (_i, [_vp]),
+    "cgl_halo_push": (_i, [_vp, _vp, _u64, _vp, _u32, _vp]),
+    "cgl_halo_wait": (_i, [_vp, _u32, _vp]),
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building first if the .so is absent and nvcc is available) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) and build_if_missing:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_cgl_b200_build", os.path.join(_PKG_DIR, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:  # noqa: BLE001
+            raise CglNativeError(f"libcgl_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(LIB_PATH):
+        raise CglNativeError(f"{LIB_PATH} not found: build it with `python {_PKG_DIR}/build.py` "
+                             "(there is no CPU fallback)")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise CglNativeError(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.cgl_abi_version() != 1:
+        raise CglNativeError("libcgl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().cgl_last_error().decode("utf-8", "replace")
+        raise CglNativeError(f"{what or 'libcgl_b200'} failed (rc={rc}): {msg}")
+
+
+def dptr(t) -> ctypes.c_void_p:
+    """Raw device (or host) pointer of a torch tensor / None."""
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def current_stream() -> ctypes.c_void_p:
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

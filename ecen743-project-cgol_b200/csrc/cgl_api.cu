@@ -1,0 +1,203 @@
+// cgl_api.cu -- error state, device queries, host-buffer entry points, IPC + halo helpers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "cgl_internal.cuh"
+
+namespace cgl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// Copy a halo strip into a peer GPU's ghost rows, then publish `seq` (release, system scope).
+__global__ void halo_push_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n_vec,
+                                 uint32_t *flag, uint32_t seq)
+{
+    for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+    }
+}
+
+__global__ void halo_wait_kernel(const uint32_t *flag, uint32_t seq)
+{
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        __nanosleep(100);
+    } while (true);
+}
+
+}  // namespace cgl
+
+using namespace cgl;
+
+extern "C" int cgl_abi_version(void) { return CGL_B200_ABI_VERSION; }
+extern "C" const char *cgl_last_error(void) { return g_err; }
+
+extern "C" int cgl_device_count(int *count_out)
+{
+    CGL_REQUIRE(count_out, CGL_E_BADARG, "cgl_device_count: null");
+    CGL_CUDA(cudaGetDeviceCount(count_out));
+    return 0;
+}
+
+extern "C" int cgl_device_info(int device, char *name_out, int name_cap, int *sm_count_out,
+                               int *cc_major_out, int *cc_minor_out, uint64_t *total_mem_out)
+{
+    cudaDeviceProp p;
+    CGL_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name_out && name_cap > 0) {
+        strncpy(name_out, p.name, (size_t)name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (sm_count_out) *sm_count_out = p.multiProcessorCount;
+    if (cc_major_out) *cc_major_out = p.major;
+    if (cc_minor_out) *cc_minor_out = p.minor;
+    if (total_mem_out) *total_mem_out = (uint64_t)p.totalGlobalMem;
+    return 0;
+}
+
+// ---- sim.__step_state_gpu replacement (CGL/CGL.py:203-208) --------------------------------
+namespace {
+struct HostStepScratch {
+    uint64_t size = 0;
+    uint8_t *cells = nullptr;
+    int8_t *stable = nullptr;
+    uint32_t *wa = nullptr, *wb = nullptr;
+    int device = -1;
+};
+thread_local HostStepScratch g_hs;
+
+int ensure_scratch(uint64_t size, uint32_t side)
+{
+    int dev = 0;
+    CGL_CUDA(cudaGetDevice(&dev));
+    if (g_hs.size >= size && g_hs.device == dev) return 0;
+    if (g_hs.cells) { cudaFree(g_hs.cells); cudaFree(g_hs.stable); cudaFree(g_hs.wa); cudaFree(g_hs.wb); }
+    g_hs = HostStepScratch();
+    const uint64_t words = (uint64_t)side * cgl_words_per_row(side);
+    CGL_CUDA(cudaMalloc(&g_hs.cells, size));
+    CGL_CUDA(cudaMalloc(&g_hs.stable, size));
+    CGL_CUDA(cudaMalloc(&g_hs.wa, words * 4));
+    CGL_CUDA(cudaMalloc(&g_hs.wb, words * 4));
+    g_hs.size = size;
+    g_hs.device = dev;
+    return 0;
+}
+}  // namespace
+
+extern "C" int cgl_step_state_gpu(uint8_t *world_host, int8_t *stable_host, uint32_t side, int spawn,
+                                  int stable_max)
+{
+    CGL_REQUIRE(world_host && stable_host && side, CGL_E_BADARG, "cgl_step_state_gpu: bad argument");
+    const uint64_t size = (uint64_t)side * side;
+    int rc = ensure_scratch(size, side);
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    CGL_CUDA(cudaMemcpyAsync(g_hs.cells, world_host, size, cudaMemcpyHostToDevice, st));
+    CGL_CUDA(cudaMemcpyAsync(g_hs.stable, stable_host, size, cudaMemcpyHostToDevice, st));
+    if ((rc = cgl_pack(g_hs.cells, g_hs.wa, 1, side, side, st))) return rc;
+    if ((rc = cgl_env_step(g_hs.wa, g_hs.wb, g_hs.stable, 1, side, nullptr, spawn, stable_max, nullptr,
+                           nullptr, nullptr, st)))
+        return rc;
+    if ((rc = cgl_unpack(g_hs.wb, g_hs.cells, 1, side, side, st))) return rc;
+    CGL_CUDA(cudaMemcpyAsync(world_host, g_hs.cells, size, cudaMemcpyDeviceToHost, st));
+    CGL_CUDA(cudaMemcpyAsync(stable_host, g_hs.stable, size, cudaMemcpyDeviceToHost, st));
+    CGL_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int cgl_env_step_host(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                                 uint32_t side, const int32_t *actions_host, int32_t *actions_dev,
+                                 int spawn, int stable_max, int32_t *reward_dev, int32_t *reward_host,
+                                 int8_t *obs_host, cgl_stream_t stream)
+{
+    CGL_REQUIRE(win && wout && stable && n_envs && side, CGL_E_BADARG, "cgl_env_step_host: bad argument");
+    CGL_REQUIRE(!actions_host || actions_dev, CGL_E_BADARG, "cgl_env_step_host: actions scratch missing");
+    CGL_REQUIRE(!reward_host || reward_dev, CGL_E_BADARG, "cgl_env_step_host: reward scratch missing");
+    cudaStream_t st = as_stream(stream);
+    if (actions_host)
+        CGL_CUDA(cudaMemcpyAsync(actions_dev, actions_host, n_envs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = cgl_env_step(win, wout, stable, n_envs, side, actions_host ? actions_dev : nullptr, spawn,
+                          stable_max, reward_host ? reward_dev : nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    if (reward_host)
+        CGL_CUDA(cudaMemcpyAsync(reward_host, reward_dev, n_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (obs_host)
+        CGL_CUDA(cudaMemcpyAsync(obs_host, stable, n_envs * (uint64_t)side * side, cudaMemcpyDeviceToHost, st));
+    CGL_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- IPC + halo ------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+extern "C" int cgl_ipc_get_handle(void *dev_ptr, uint8_t handle_out[64])
+{
+    CGL_REQUIRE(dev_ptr && handle_out, CGL_E_BADARG, "cgl_ipc_get_handle: null");
+    cudaIpcMemHandle_t h;
+    CGL_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+extern "C" int cgl_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out)
+{
+    CGL_REQUIRE(handle && dev_ptr_out, CGL_E_BADARG, "cgl_ipc_open_handle: null");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CGL_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int cgl_ipc_close_handle(void *dev_ptr)
+{
+    CGL_REQUIRE(dev_ptr, CGL_E_BADARG, "cgl_ipc_close_handle: null");
+    CGL_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+extern "C" int cgl_halo_push(const uint32_t *src, uint32_t *peer_dst, uint64_t n_words,
+                             uint32_t *peer_flag, uint32_t seq, cgl_stream_t stream)
+{
+    CGL_REQUIRE(src && peer_dst && peer_flag && n_words && n_words % 4 == 0, CGL_E_BADARG,
+                "cgl_halo_push: bad argument (n_words must be a multiple of 4)");
+    halo_push_kernel<<<1, 1024, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src),
+                                                        reinterpret_cast<uint4 *>(peer_dst), n_words / 4,
+                                                        peer_flag, seq);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_halo_wait(const uint32_t *flag, uint32_t seq, cgl_stream_t stream)
+{
+    CGL_REQUIRE(flag, CGL_E_BADARG, "cgl_halo_wait: null");
+    halo_wait_kernel<<<1, 1, 0, as_stream(stream)>>>(flag, seq);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,147 @@
+// cgl_bits.cuh -- bit-sliced B3/S23 logic and the SIMD-in-register int8 stability rule.
+//
+// Everything here is `__host__ __device__` so the exact expressions the sm_100a kernels
+// execute are also compiled by g++ into tests/twin/ (CPU-box unit tests of the bit logic).
+//
+// Layout convention (whole repo): a world row is ceil(cols/32) uint32 words; bit j of word w is
+// the cell at column 32*w + j; padding bits above `cols` in the last word are ZERO.
+//
+// Semantics restated from the reference kernel `run`, /root/reference/CGL/CGL.py:147-181
+// (CPU twin :211-243):
+//   n    = sum of the 8 torus neighbours                         (:162-165)
+//   next = (n == 3) || (n == 2 && prev)                          (:168-170)
+//   stable' = surv ? (s == STABLE ? s : int8(s + 1)) : born ? SPAWN : 0      (:177-179)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CGL_HD __host__ __device__ __forceinline__
+#else
+#define CGL_HD inline
+#endif
+
+namespace cgl {
+
+// ---- horizontal neighbour planes ------------------------------------------------------
+// west(c)[j] = cell at column-1, east(c)[j] = cell at column+1, for an interior word.
+CGL_HD uint32_t west_plane(uint32_t prev_word, uint32_t c) { return (c << 1) | (prev_word >> 31); }
+CGL_HD uint32_t east_plane(uint32_t c, uint32_t next_word) { return (c >> 1) | (next_word << 31); }
+
+// Horizontal partial sums of one row (2 bit-planes each):
+//   t = west + east           (centre excluded; used for the cell's own row)
+//   s = west + centre + east  (used for the rows above and below)
+struct HSum { uint32_t s0, s1, t0, t1; };
+
+CGL_HD HSum hsum(uint32_t w, uint32_t c, uint32_t e)
+{
+    HSum h;
+    h.t0 = w ^ e;
+    h.t1 = w & e;
+    h.s0 = h.t0 ^ c;
+    h.s1 = h.t1 | (h.t0 & c);
+    return h;
+}
+
+CGL_HD uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+// n = up.s + mid.t + dn.s  in 0..8;   n = x0 + 2*(up.s1 + dn.s1 + mid.t1 + carry0)
+// next = (#weight-2 terms == 1) & (x0 | centre)         [n==3 -> x0=1 ; n==2 -> needs centre]
+CGL_HD uint32_t life_rule(const HSum &up, const HSum &mid, const HSum &dn, uint32_t centre)
+{
+    uint32_t x0 = up.s0 ^ dn.s0 ^ mid.t0;
+    uint32_t c0 = maj3(up.s0, dn.s0, mid.t0);
+    uint32_t f1 = up.s1 ^ dn.s1 ^ mid.t1;           // low bit of (up.s1 + dn.s1 + mid.t1)
+    uint32_t f2 = maj3(up.s1, dn.s1, mid.t1);       // high bit
+    uint32_t one = ~f2 & (f1 ^ c0);                 // (that sum + carry0) == 1
+    return one & (x0 | centre);
+}
+
+// Full 3x3 evaluation from 9 already-shifted-independent words (generic path).
+//   rows: a = above, c = current, b = below; each with its west/east adjacent WORDS.
+CGL_HD uint32_t life_word(uint32_t aw, uint32_t a, uint32_t ae,
+                          uint32_t cw, uint32_t c, uint32_t ce,
+                          uint32_t bw, uint32_t b, uint32_t be)
+{
+    return life_rule(hsum(aw, a, ae), hsum(cw, c, ce), hsum(bw, b, be), c);
+}
+
+// ---- generic row access: torus columns for an arbitrary `cols` -----------------------------
+// The last word of a row holds `rbits` valid bits (1..32); the column left of column 0 is
+// column cols-1 and vice versa (CGL/CGL.py:156-157).  W == 1 makes prev == next == the word itself.
+struct RowPlanes { uint32_t west, c, east; };
+
+CGL_HD RowPlanes load_row_planes(const uint32_t *row, uint32_t w, uint32_t W, uint32_t rbits)
+{
+    RowPlanes p;
+    p.c = row[w];
+    uint32_t prev = row[w == 0 ? W - 1 : w - 1];
+    const uint32_t next = row[w == W - 1 ? 0 : w + 1];
+    if (w == 0) prev <<= (32 - rbits);                      // last valid column -> bit 31
+    p.west = west_plane(prev, p.c);
+    p.east = (w == W - 1) ? ((p.c >> 1) | ((next & 1u) << (rbits - 1))) : east_plane(p.c, next);
+    return p;
+}
+
+// ---- SIMD-in-register int8 stability rule (4 cells per 32-bit word) --------------------
+// Per byte: (x != MAX) ? x + 1 : x, with int8 wrap-around and no carry between bytes.
+//   max4 = stable_max replicated into the 4 bytes.
+CGL_HD uint32_t inc_unless_max4(uint32_t s, uint32_t max4)
+{
+    uint32_t x = s ^ max4;                                           // byte == 0  <=>  s == MAX
+    uint32_t ne7 = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // bit7 = (byte != 0)
+    uint32_t inc = ne7 >> 7;                                         // 0/1 per byte
+    uint32_t lo = (s & 0x7f7f7f7fu) + inc;                           // carry stops at bit 7
+    return lo ^ (s & 0x80808080u);
+}
+
+// stable' for 4 cells given byte masks: surv_mask (0xFF where alive->alive) and
+// born_spawn (SPAWN byte where dead->alive, 0 elsewhere); everything else becomes 0.
+CGL_HD uint32_t stable_update4(uint32_t s, uint32_t surv_mask, uint32_t born_spawn, uint32_t max4)
+{
+    return (inc_unless_max4(s, max4) & surv_mask) | born_spawn;
+}
+
+// Expand a 4-bit nibble to 4 byte masks (bit i -> byte i = 0xFF).
+CGL_HD uint32_t nibble_to_bytemask(uint32_t nib)
+{
+    uint32_t spread = (nib * 0x00204081u) & 0x01010101u;             // bit i -> bit 8*i
+    return spread * 0xFFu;
+}
+
+// Scalar form of the rule (generic per-cell path); identical to CGL/CGL.py:236-242.
+CGL_HD int8_t stable_update1(int8_t s, bool prev, bool next, int8_t spawn, int8_t stable_max)
+{
+    if (next && prev) return (s != stable_max) ? (int8_t)(s + 1) : s;
+    if (next) return spawn;
+    return 0;
+}
+
+// Interleave the nibbles of `cur` and `nxt` (32 cells) into 8 LUT-index bytes
+// ((cur_nibble << 4) | nxt_nibble), ordered so that out[0] serves cells 0..15 and out[1]
+// serves cells 16..31, byte k of out[h] <-> cells 16h + 4k .. 16h + 4k + 3.
+CGL_HD void mix_nibbles(uint32_t cur, uint32_t nxt, uint32_t &out_lo, uint32_t &out_hi)
+{
+    uint32_t even = (nxt & 0x0f0f0f0fu) | ((cur & 0x0f0f0f0fu) << 4);   // byte m <-> nibble 2m
+    uint32_t odd = ((nxt >> 4) & 0x0f0f0f0fu) | (cur & 0xf0f0f0f0u);    // byte m <-> nibble 2m+1
+#if defined(__CUDA_ARCH__)
+    out_lo = __byte_perm(even, odd, 0x5140);     // e0 o0 e1 o1
+    out_hi = __byte_perm(even, odd, 0x7362);     // e2 o2 e3 o3
+#else
+    out_lo = (even & 0xffu) | ((odd & 0xffu) << 8) | ((even & 0xff00u) << 8) | ((odd & 0xff00u) << 16);
+    out_hi = ((even >> 16) & 0xffu) | (((odd >> 16) & 0xffu) << 8) | (((even >> 24) & 0xffu) << 16) |
+             (((odd >> 24) & 0xffu) << 24);
+#endif
+}
+
+// LUT entry for index byte (cur_nibble << 4) | nxt_nibble:  .x = surv byte mask,
+// .y = born byte mask & SPAWN replicated.
+CGL_HD void lut_entry(uint32_t idx, uint32_t spawn4, uint32_t &surv_mask, uint32_t &born_spawn)
+{
+    uint32_t cur = idx >> 4, nxt = idx & 0xfu;
+    surv_mask = nibble_to_bytemask(cur & nxt);
+    born_spawn = nibble_to_bytemask(nxt & ~cur & 0xfu) & spawn4;
+}
+
+CGL_HD uint32_t rep4(int v) { return (uint32_t)(uint8_t)v * 0x01010101u; }
+
+}  // namespace cgl

@@ -1,0 +1,548 @@
+// cgl_env.cu -- the env step (toggle -> generation -> int8 stability -> reward) for sm_100a.
+//
+// Reference semantics: kernel `run` /root/reference/CGL/CGL.py:147-181, its driver
+// `__step_state_gpu` :203-208, toggle_state :322-328, reward :255-256, alive :259-260.
+// Nothing here is translated from that kernel (one thread per byte cell, 10 byte loads, 4 integer
+// modulos): state is 1 bit per cell + 1 int8 per cell, the generation is bit-sliced LOP3 logic on
+// 32 cells per instruction, and the stability plane is streamed once with 128-bit accesses and
+// updated 4 cells per instruction.
+#include "cgl_internal.cuh"
+
+namespace cgl {
+
+// =========================================================================================
+// Fused fast path: side % 32 == 0, side <= 256.  One CTA handles EPC environments, TPE threads
+// each.  HBM traffic per env: world 2 * side^2/8 B, stability 2 * side^2 B  (2.25 B / cell).
+//
+//   phase 0  the first batch of stability uint4 loads is issued (independent of the bits)
+//   phase A  world words -> shared memory (uint4, coalesced), action bit flipped on the way
+//   phase B  next generation from shared memory (9 LDS + ~12 LOP3 per 32 cells), stored to
+//            HBM; (cur,next) nibbles interleaved into one LUT-index byte per 4 cells
+//   phase C  stability stream: LDG.128 -> 4 x {LDS.64 mask LUT, byte-SIMD update, IDP.4A}
+//            -> STG.128; reward reduced with REDUX + one shared atomic per warp
+// =========================================================================================
+template <int S>
+struct EnvCfg {
+    static constexpr int W = S / 32;              // words per row
+    static constexpr int WPE = S * W;             // words per env
+    static constexpr int SIZE = S * S;            // cells per env
+    static constexpr int NCHUNK = SIZE / 16;      // 16-cell (uint4) stability chunks per env
+    static constexpr int TPE = (S <= 64) ? 32 : S;          // threads per env
+    static constexpr int EPC = (TPE >= 128) ? 1 : (128 / TPE);  // envs per CTA
+    static constexpr int THREADS = TPE * EPC;
+    static constexpr int CPT = NCHUNK / TPE;      // chunks per thread
+    static constexpr int UNR = CPT < 8 ? CPT : 8; // chunks in flight per thread
+    static constexpr int SMEM = 256 * 8 + EPC * (WPE * 4 + WPE * 8) + EPC * 8;
+    static_assert(S % 32 == 0 && NCHUNK % TPE == 0 && WPE % 4 == 0, "unsupported side");
+};
+
+template <int S>
+__global__ void __launch_bounds__(EnvCfg<S>::THREADS)
+env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out,
+                      int8_t *__restrict__ stable, uint32_t n_envs,
+                      const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
+                      int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
+                      int *__restrict__ err_flag)
+{
+    using C = EnvCfg<S>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *lut = reinterpret_cast<uint2 *>(smem_raw);
+    const int g = threadIdx.x / C::TPE;           // env slot in this CTA
+    const int t = threadIdx.x % C::TPE;
+    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw + 2048) + g * (C::WPE * 3);
+    uint32_t *mix = cur + C::WPE;                 // 2 words per world word
+    int *red = reinterpret_cast<int *>(smem_raw + 2048 + C::EPC * C::WPE * 12) + g * 2;
+
+    const uint32_t e = blockIdx.x * C::EPC + g;
+    const bool active = e < n_envs;
+
+    // ---- phase 0: stability loads in flight before anything else --------------------------
+    uint4 *sp = reinterpret_cast<uint4 *>(stable + (size_t)e * C::SIZE);
+    uint4 sreg[C::UNR];
+    if (active) {
+#pragma unroll
+        for (int u = 0; u < C::UNR; ++u) sreg[u] = sp[t + u * C::TPE];
+    }
+
+    for (int i = threadIdx.x; i < 256; i += C::THREADS) {
+        uint32_t sm, bs;
+        lut_entry((uint32_t)i, spawn4, sm, bs);
+        lut[i] = make_uint2(sm, bs);
+    }
+    if (t == 0) { red[0] = 0; red[1] = 0; }
+
+    // ---- action decode (toggle_state before step, CGL/main.py:66-67) ----------------------
+    int act = -1;                                 // -1: nothing to toggle
+    if (active && actions != nullptr) {
+        int a = actions[e];
+        if (a >= 0 && a < C::SIZE) act = a;
+        else if (a != C::SIZE && t == 0 && err_flag != nullptr) atomicOr(err_flag, 1);
+    }
+    // cell index == bit index because a row is exactly W full words
+    const int act_word = act >> 5;
+    const uint32_t act_bit = 1u << (act & 31);
+
+    // ---- phase A: world -> smem ------------------------------------------------------------
+    if (active) {
+        const uint4 *wp = reinterpret_cast<const uint4 *>(world_in + (size_t)e * C::WPE);
+        for (int i = t; i < C::WPE / 4; i += C::TPE) {
+            uint4 v = __ldg(wp + i);
+            if (act >= 0 && (act_word >> 2) == i) {
+                int k = act_word & 3;
+                if (k == 0) v.x ^= act_bit; else if (k == 1) v.y ^= act_bit;
+                else if (k == 2) v.z ^= act_bit; else v.w ^= act_bit;
+            }
+            reinterpret_cast<uint4 *>(cur)[i] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: next generation ------------------------------------------------------------
+    uint32_t pop = 0;
+    if (active) {
+        uint32_t *wo = world_out + (size_t)e * C::WPE;
+#pragma unroll
+        for (int j = 0; j < C::WPE / C::TPE; ++j) {
+            const int i = t + j * C::TPE;
+            const int r = i / C::W, w = i % C::W;
+            const int ru = (r == 0 ? S - 1 : r - 1) * C::W, rc = r * C::W,
+                      rd = (r == S - 1 ? 0 : r + 1) * C::W;
+            const int wl = (w == 0 ? C::W - 1 : w - 1), wr = (w == C::W - 1 ? 0 : w + 1);
+            const uint32_t a = cur[ru + w], c = cur[rc + w], b = cur[rd + w];
+            const HSum ha = hsum(west_plane(cur[ru + wl], a), a, east_plane(a, cur[ru + wr]));
+            const HSum hc = hsum(west_plane(cur[rc + wl], c), c, east_plane(c, cur[rc + wr]));
+            const HSum hb = hsum(west_plane(cur[rd + wl], b), b, east_plane(b, cur[rd + wr]));
+            const uint32_t nxt = life_rule(ha, hc, hb, c);
+            wo[i] = nxt;
+            pop += __popc(nxt);
+            uint32_t lo, hi;
+            mix_nibbles(c, nxt, lo, hi);
+            reinterpret_cast<uint2 *>(mix)[i] = make_uint2(lo, hi);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: stability stream + reward -------------------------------------------------
+    int acc = 0;
+    if (active) {
+        const int act_chunk = act >> 4;                      // -1 when no action
+        const int act_sub = (act >> 2) & 3;
+        const uint32_t act_mask = 0xffu << ((act & 3) * 8);
+#pragma unroll
+        for (int b0 = 0; b0 < C::CPT; b0 += C::UNR) {
+            if (b0 > 0) {
+#pragma unroll
+                for (int u = 0; u < C::UNR; ++u)
+                    if (b0 + u < C::CPT) sreg[u] = sp[t + (b0 + u) * C::TPE];
+            }
+#pragma unroll
+            for (int u = 0; u < C::UNR; ++u) {
+                if (b0 + u >= C::CPT) continue;
+                const int q = t + (b0 + u) * C::TPE;
+                uint32_t s[4] = {sreg[u].x, sreg[u].y, sreg[u].z, sreg[u].w};
+                if (q == act_chunk) {                        // stable[action] = spawn (CGL.py:326)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k == act_sub) s[k] = (s[k] & ~act_mask) | (spawn4 & act_mask);
+                }
+                const uint32_t m = mix[q];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint2 l = lut[(m >> (8 * k)) & 0xffu];
+                    s[k] = stable_update4(s[k], l.x, l.y, max4);
+                    acc = __dp4a((int)s[k], 0x01010101, acc);
+                }
+                sp[q] = make_uint4(s[0], s[1], s[2], s[3]);
+            }
+        }
+    }
+    if (reward_out != nullptr || alive_out != nullptr) {
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        pop = __reduce_add_sync(0xffffffffu, pop);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&red[0], acc);
+            atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
+        }
+        __syncthreads();
+        if (active && t == 0) {
+            if (reward_out != nullptr) reward_out[e] = red[0];
+            if (alive_out != nullptr) alive_out[e] = (uint32_t)red[1];
+        }
+    }
+}
+
+template <int S>
+static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                            const int32_t *actions, int spawn, int stable_max, int32_t *reward,
+                            uint32_t *alive, int *err, cudaStream_t st)
+{
+    using C = EnvCfg<S>;
+    const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
+    env_step_fused_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(
+        win, wout, stable, (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive,
+        err);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+// =========================================================================================
+// Generic path: any side >= 1, any batch.  Three small kernels (toggle, generation, stability).
+// =========================================================================================
+
+// One thread per env; indices of one env are handled sequentially so that a duplicated index
+// toggles once (numpy gather-then-scatter, CGL/CGL.py:325).
+__global__ void toggle_kernel(uint32_t *__restrict__ world, int8_t *__restrict__ stable,
+                              uint64_t n_envs, uint32_t side, uint32_t W,
+                              const int32_t *__restrict__ idx, uint32_t k, int8_t spawn,
+                              int *__restrict__ err_flag)
+{
+    const uint64_t size = (uint64_t)side * side;
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_envs;
+         e += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t *my = idx + e * k;
+        for (uint32_t j = 0; j < k; ++j) {
+            const int64_t a = my[j];
+            if (a < 0 || (uint64_t)a > size) {
+                if (err_flag != nullptr) atomicOr(err_flag, 1);
+                continue;
+            }
+            if ((uint64_t)a == size) continue;               // "do nothing" action
+            bool dup = false;
+            for (uint32_t j2 = 0; j2 < j; ++j2) dup |= (my[j2] == my[j]);
+            if (dup) continue;
+            const uint32_t r = (uint32_t)((uint64_t)a / side), c = (uint32_t)((uint64_t)a % side);
+            world[(e * side + r) * W + (c >> 5)] ^= 1u << (c & 31);
+            stable[e * size + a] = spawn;                    // even when toggled to dead (N2)
+        }
+    }
+}
+
+// One thread per packed word.  wrap_rows: torus rows (reference) or dead rows outside (bands).
+__global__ void life_generic_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                    uint64_t n_envs, uint32_t rows, uint32_t cols, uint32_t W,
+                                    int wrap_rows, uint32_t *__restrict__ alive_out)
+{
+    const uint64_t wpe = (uint64_t)rows * W;
+    const uint64_t total = n_envs * wpe;
+    const uint32_t rbits = cols - 32 * (W - 1);
+    const uint32_t last_mask = rbits == 32 ? 0xffffffffu : ((1u << rbits) - 1u);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = i / wpe;
+        const uint32_t rem = (uint32_t)(i - e * wpe);
+        const uint32_t r = rem / W, w = rem - r * W;
+        const uint32_t *base = in + e * wpe;
+        const RowPlanes pc = load_row_planes(base + (uint64_t)r * W, w, W, rbits);
+        RowPlanes pa = {0, 0, 0}, pb = {0, 0, 0};
+        if (r > 0) pa = load_row_planes(base + (uint64_t)(r - 1) * W, w, W, rbits);
+        else if (wrap_rows) pa = load_row_planes(base + (uint64_t)(rows - 1) * W, w, W, rbits);
+        if (r + 1 < rows) pb = load_row_planes(base + (uint64_t)(r + 1) * W, w, W, rbits);
+        else if (wrap_rows) pb = load_row_planes(base, w, W, rbits);
+        uint32_t nxt = life_rule(hsum(pa.west, pa.c, pa.east), hsum(pc.west, pc.c, pc.east),
+                                 hsum(pb.west, pb.c, pb.east), pc.c);
+        if (w == W - 1) nxt &= last_mask;
+        out[i] = nxt;
+        if (alive_out != nullptr) {
+            // envs are contiguous: reduce over the lanes that share this env, one atomic each
+            const unsigned peers = __match_any_sync(__activemask(), e);
+            const unsigned total_pop = __reduce_add_sync(peers, (unsigned)__popc(nxt));
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(alive_out + e, total_pop);
+        }
+    }
+}
+
+// One thread per cell: scalar form of the stability rule (CGL/CGL.py:236-242).
+__global__ void stable_generic_kernel(const uint32_t *__restrict__ prev, const uint32_t *__restrict__ next,
+                                      int8_t *__restrict__ stable, uint64_t n_envs, uint32_t side,
+                                      uint32_t W, int8_t spawn, int8_t stable_max,
+                                      int32_t *__restrict__ reward_out)
+{
+    const uint64_t size = (uint64_t)side * side;
+    const uint64_t total = n_envs * size;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = i / size;
+        const uint64_t cell = i - e * size;
+        const uint32_t r = (uint32_t)(cell / side), c = (uint32_t)(cell - (uint64_t)r * side);
+        const uint64_t widx = (e * side + r) * W + (c >> 5);
+        const bool p = (prev[widx] >> (c & 31)) & 1u;
+        const bool n = (next[widx] >> (c & 31)) & 1u;
+        const int8_t s = stable_update1(stable[i], p, n, spawn, stable_max);
+        stable[i] = s;
+        if (reward_out != nullptr) {
+            const unsigned peers = __match_any_sync(__activemask(), e);
+            const int sum = __reduce_add_sync(peers, (int)s);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(reward_out + e, sum);
+        }
+    }
+}
+
+// =========================================================================================
+// Layout conversion and reductions
+// =========================================================================================
+
+// One warp builds 32 consecutive packed words; lane j reads the j-th cell of each word
+// (coalesced 32-byte reads), __ballot_sync assembles the word, lane k keeps word k.
+__global__ void pack_kernel(const uint8_t *__restrict__ cells, uint32_t *__restrict__ world,
+                            uint64_t n_envs, uint32_t rows, uint32_t cols, uint32_t W)
+{
+    const uint64_t total_words = n_envs * rows * W;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < total_words; base += n_warps * 32) {
+        uint32_t mine = 0;
+        for (uint32_t k = 0; k < 32; ++k) {
+            const uint64_t widx = base + k;
+            uint32_t bit = 0;
+            if (widx < total_words) {
+                const uint64_t row = widx / W;               // global row index (e * rows + r)
+                const uint32_t w = (uint32_t)(widx - row * W);
+                const uint32_t col = w * 32 + lane;
+                if (col < cols) bit = cells[row * cols + col] != 0;
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, bit);
+            if (lane == k) mine = word;
+        }
+        if (base + lane < total_words) world[base + lane] = mine;
+    }
+}
+
+// One thread per cell.  mode 0: cells = bit.  mode 1: stable = bit ? spawn : 0.
+__global__ void unpack_kernel(const uint32_t *__restrict__ world, uint8_t *__restrict__ cells,
+                              uint64_t n_envs, uint32_t rows, uint32_t cols, uint32_t W,
+                              int mode, uint8_t spawn)
+{
+    const uint64_t total = n_envs * rows * cols;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = i / cols;
+        const uint32_t c = (uint32_t)(i - row * cols);
+        const uint32_t bit = (world[row * W + (c >> 5)] >> (c & 31)) & 1u;
+        cells[i] = mode == 0 ? (uint8_t)bit : (bit ? spawn : (uint8_t)0);
+    }
+}
+
+// blockIdx.y = env; blocks along x stride over the env's bytes; one atomic per block.
+__global__ void reward_kernel(const int8_t *__restrict__ stable, uint64_t size,
+                              int32_t *__restrict__ reward_out)
+{
+    const int8_t *s = stable + (uint64_t)blockIdx.y * size;
+    int acc = 0;
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(s);
+        const uint64_t nvec = size / 16;
+        for (uint64_t i = tid; i < nvec; i += nthr) {
+            const uint4 x = __ldg(v + i);
+            acc = __dp4a((int)x.x, 0x01010101, acc);
+            acc = __dp4a((int)x.y, 0x01010101, acc);
+            acc = __dp4a((int)x.z, 0x01010101, acc);
+            acc = __dp4a((int)x.w, 0x01010101, acc);
+        }
+        for (uint64_t i = nvec * 16 + tid; i < size; i += nthr) acc += s[i];
+    } else {
+        for (uint64_t i = tid; i < size; i += nthr) acc += s[i];
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    __shared__ int block_acc;
+    if (threadIdx.x == 0) block_acc = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(&block_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_acc != 0) atomicAdd(reward_out + blockIdx.y, block_acc);
+}
+
+__global__ void alive_kernel(const uint32_t *__restrict__ world, uint64_t wpe,
+                             uint32_t *__restrict__ alive_out)
+{
+    const uint32_t *w = world + (uint64_t)blockIdx.y * wpe;
+    unsigned acc = 0;
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < wpe; i += nthr) acc += __popc(__ldg(w + i));
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    __shared__ unsigned block_acc;
+    if (threadIdx.x == 0) block_acc = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(&block_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_acc != 0) atomicAdd(alive_out + blockIdx.y, block_acc);
+}
+
+__global__ void set_int_kernel(int *p, int v) { *p = v; }
+
+__global__ void match_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                             uint64_t n_words, int *__restrict__ equal_out)
+{
+    bool diff = false;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        diff |= (a[i] != b[i]);
+    if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicAnd(equal_out, 0);
+}
+
+}  // namespace cgl
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace cgl;
+
+extern "C" uint32_t cgl_words_per_row(uint32_t cols) { return (cols + 31) / 32; }
+
+extern "C" int cgl_env_step_is_fused(uint32_t side) { return side % 32 == 0 && side >= 32 && side <= 256; }
+
+extern "C" int cgl_env_step_launches(uint32_t side, int has_actions)
+{
+    return cgl_env_step_is_fused(side) ? 1 : (2 + (has_actions ? 1 : 0));
+}
+
+extern "C" int cgl_pack(const uint8_t *cells, uint32_t *world, uint64_t n_envs, uint32_t rows,
+                        uint32_t cols, cgl_stream_t stream)
+{
+    CGL_REQUIRE(cells && world && n_envs && rows && cols, CGL_E_BADARG, "cgl_pack: bad argument");
+    const uint32_t W = cgl_words_per_row(cols);
+    const uint64_t words = n_envs * rows * W;
+    pack_kernel<<<grid_for(words, 256), 256, 0, as_stream(stream)>>>(cells, world, n_envs, rows, cols, W);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_unpack(const uint32_t *world, uint8_t *cells, uint64_t n_envs, uint32_t rows,
+                          uint32_t cols, cgl_stream_t stream)
+{
+    CGL_REQUIRE(cells && world && n_envs && rows && cols, CGL_E_BADARG, "cgl_unpack: bad argument");
+    const uint64_t total = n_envs * rows * cols;
+    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        world, cells, n_envs, rows, cols, cgl_words_per_row(cols), 0, 0);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_init_stable(const uint32_t *world, int8_t *stable, uint64_t n_envs, uint32_t side,
+                               int spawn, cgl_stream_t stream)
+{
+    CGL_REQUIRE(stable && world && n_envs && side, CGL_E_BADARG, "cgl_init_stable: bad argument");
+    const uint64_t total = n_envs * side * side;
+    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
+        (uint8_t)(int8_t)spawn);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_toggle(uint32_t *world, int8_t *stable, uint64_t n_envs, uint32_t side,
+                          const int32_t *idx, uint32_t k, int spawn, int *err_flag,
+                          cgl_stream_t stream)
+{
+    CGL_REQUIRE(world && stable && n_envs && side && idx, CGL_E_BADARG, "cgl_toggle: bad argument");
+    if (k == 0) return 0;
+    toggle_kernel<<<grid_for(n_envs, 128), 128, 0, as_stream(stream)>>>(
+        world, stable, n_envs, side, cgl_words_per_row(side), idx, k, (int8_t)spawn, err_flag);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,
+                             uint32_t cols, int wrap_rows, uint32_t *alive_out, cgl_stream_t stream);
+
+extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                            uint32_t side, const int32_t *actions, int spawn, int stable_max,
+                            int32_t *reward, uint32_t *alive, int *err, cgl_stream_t stream)
+{
+    CGL_REQUIRE(win && wout && stable && n_envs && side, CGL_E_BADARG, "cgl_env_step: bad argument");
+    CGL_REQUIRE(win != wout, CGL_E_BADARG, "cgl_env_step: world_in and world_out must not alias");
+    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step: n_envs too large");
+    cudaStream_t st = as_stream(stream);
+    if (cgl_env_step_is_fused(side)) {
+#define CGL_CASE(S)                                                                               \
+    case S:                                                                                       \
+        return launch_env_fused<S>(win, wout, stable, n_envs, actions, spawn, stable_max, reward, \
+                                   alive, err, st)
+        switch (side) {
+            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
+            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
+        }
+#undef CGL_CASE
+    }
+    // generic: toggle -> generation -> stability
+    const uint32_t W = cgl_words_per_row(side);
+    if (actions != nullptr) {
+        int rc = cgl_toggle(win, stable, n_envs, side, actions, 1, spawn, err, stream);
+        if (rc) return rc;
+    }
+    int rc = cgl_life_step(win, wout, n_envs, side, side, 1, alive, stream);
+    if (rc) return rc;
+    if (reward != nullptr) CGL_CUDA(cudaMemsetAsync(reward, 0, n_envs * sizeof(int32_t), st));
+    const uint64_t total = n_envs * side * side;
+    stable_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+        win, wout, stable, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_life_step_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,
+                                     uint32_t cols, int wrap_rows, uint32_t *alive_out,
+                                     cgl_stream_t stream)
+{
+    CGL_REQUIRE(in && out && n_envs && rows && cols && in != out, CGL_E_BADARG,
+                "cgl_life_step: bad argument");
+    cudaStream_t st = as_stream(stream);
+    const uint32_t W = cgl_words_per_row(cols);
+    if (alive_out != nullptr) CGL_CUDA(cudaMemsetAsync(alive_out, 0, n_envs * sizeof(uint32_t), st));
+    const uint64_t words = n_envs * rows * W;
+    life_generic_kernel<<<grid_for(words, 256), 256, 0, st>>>(in, out, n_envs, rows, cols, W,
+                                                             wrap_rows, alive_out);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_reward(const int8_t *stable, uint64_t n_envs, uint64_t size, int32_t *reward_out,
+                          cgl_stream_t stream)
+{
+    CGL_REQUIRE(stable && n_envs && size && reward_out && n_envs <= 65535 * 1024ull, CGL_E_BADARG,
+                "cgl_reward: bad argument");
+    cudaStream_t st = as_stream(stream);
+    CGL_CUDA(cudaMemsetAsync(reward_out, 0, n_envs * sizeof(int32_t), st));
+    const unsigned threads = 256;
+    uint64_t bx = (size / 16 + threads * 4 - 1) / (threads * 4);
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+    for (uint64_t e0 = 0; e0 < n_envs; e0 += 65535) {        // gridDim.y limit
+        const unsigned ny = (unsigned)((n_envs - e0) < 65535 ? (n_envs - e0) : 65535);
+        reward_kernel<<<dim3((unsigned)bx, ny), threads, 0, st>>>(stable + e0 * size, size, reward_out + e0);
+        CGL_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int cgl_alive(const uint32_t *world, uint64_t n_envs, uint64_t wpe, uint32_t *alive_out,
+                         cgl_stream_t stream)
+{
+    CGL_REQUIRE(world && n_envs && wpe && alive_out, CGL_E_BADARG, "cgl_alive: bad argument");
+    cudaStream_t st = as_stream(stream);
+    CGL_CUDA(cudaMemsetAsync(alive_out, 0, n_envs * sizeof(uint32_t), st));
+    const unsigned threads = 256;
+    uint64_t bx = (wpe + threads * 4 - 1) / (threads * 4);
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+    for (uint64_t e0 = 0; e0 < n_envs; e0 += 65535) {
+        const unsigned ny = (unsigned)((n_envs - e0) < 65535 ? (n_envs - e0) : 65535);
+        alive_kernel<<<dim3((unsigned)bx, ny), threads, 0, st>>>(world + e0 * wpe, wpe, alive_out + e0);
+        CGL_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int cgl_match(const uint32_t *a, const uint32_t *b, uint64_t n_words, int *equal_out,
+                         cgl_stream_t stream)
+{
+    CGL_REQUIRE(a && b && n_words && equal_out, CGL_E_BADARG, "cgl_match: bad argument");
+    cudaStream_t st = as_stream(stream);
+    set_int_kernel<<<1, 1, 0, st>>>(equal_out, 1);
+    match_kernel<<<grid_for(n_words, 256), 256, 0, st>>>(a, b, n_words, equal_out);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,156 @@
+/*
+ * cgl_b200.h -- C ABI of libcgl_b200.so: the B200-native (sm_100a) Game-of-Life env step.
+ *
+ * This is the drop-in boundary for the hot path of BADBEEF6502/ECEN743-Project-CGoL
+ * (class `sim`, /root/reference/CGL/CGL.py).  The reference has no FFI of its own: its device
+ * path is a PyCUDA kernel string (`run`, CGL/CGL.py:146-182) plus four memcpys
+ * (`__step_state_gpu`, CGL/CGL.py:203-208).  Every entry point below cites the reference
+ * lines it replaces.  Plain pointers and sizes only -- no torch / numpy types.  The Python
+ * host (ecen743-project-cgol_b200/CGL.py, cgl_b200/) binds it with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - "device" pointers are CUDA device pointers on the current device; all device entry points
+ *     are asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy default).
+ *   - world plane, bit-packed: per env `rows` rows of W = ceil(cols/32) uint32 words;
+ *     bit j of word w = cell at column 32*w + j; padding bits are zero.  Batch = [n_envs][rows][W].
+ *   - stable plane: int8 [n_envs][rows*cols], the reference's own row-major order
+ *     (it IS the observation, CGL/CGL.py:281-285).
+ *   - return value: 0 on success; >0 = cudaError_t; <0 = CGL_E_* argument error.
+ *     cgl_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef CGL_B200_H
+#define CGL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGL_B200_ABI_VERSION 1
+
+#define CGL_E_BADARG   (-1)   /* null pointer / zero size / unsupported shape */
+#define CGL_E_BADINDEX (-2)   /* toggle index outside [0, size] (host-buffer entry points only) */
+#define CGL_E_NOMEM    (-3)
+
+typedef void *cgl_stream_t;
+
+int cgl_abi_version(void);
+const char *cgl_last_error(void);
+
+/* Number of CUDA devices / name + SM count of `device` (replaces the device banner query,
+ * CGL/CGL.py:120-140).  name_out may be NULL. */
+int cgl_device_count(int *count_out);
+int cgl_device_info(int device, char *name_out, int name_cap, int *sm_count_out,
+                    int *cc_major_out, int *cc_minor_out, uint64_t *total_mem_out);
+
+/* uint32 words per packed row. */
+uint32_t cgl_words_per_row(uint32_t cols);
+
+/* ---- layout conversion at the API boundary ---------------------------------------------
+ * pack:   cells uint8 [n_envs][rows*cols] (nonzero = alive) -> packed world.
+ * unpack: packed world -> cells uint8 {0,1}.     (reference array format: CGL/CGL.py:94,107) */
+int cgl_pack(const uint8_t *cells_dev, uint32_t *world_dev, uint64_t n_envs, uint32_t rows,
+             uint32_t cols, cgl_stream_t stream);
+int cgl_unpack(const uint32_t *world_dev, uint8_t *cells_dev, uint64_t n_envs, uint32_t rows,
+               uint32_t cols, cgl_stream_t stream);
+
+/* stable = alive ? spawn : 0   (constructor, CGL/CGL.py:111-112). */
+int cgl_init_stable(const uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_t side,
+                    int spawn, cgl_stream_t stream);
+
+/* ---- sim.toggle_state, CGL/CGL.py:322-328 -------------------------------------------------
+ * idx_dev: int32 [n_envs][k].  For every env: each DISTINCT valid index in its row is toggled
+ * once (numpy gather-then-scatter semantics) and stable[idx] = spawn.  idx == side*side is the
+ * "do nothing" action; anything else out of range is skipped and sets *err_flag_dev |= 1
+ * (err_flag_dev may be NULL). */
+int cgl_toggle(uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_t side,
+               const int32_t *idx_dev, uint32_t k, int spawn, int *err_flag_dev,
+               cgl_stream_t stream);
+
+/* ---- the env step: toggle (optional) -> generation -> stability -> reward ----------------
+ * Replaces kernel `run` (CGL/CGL.py:147-181) + `__step_state_gpu` (:203-208) + reward()
+ * (:255-256) + alive() (:259-260) for n_envs independent environments, fused in one launch on
+ * the fast path (side % 32 == 0, side <= 512) and three launches otherwise.
+ *   world_in_dev   packed world at t.  Scratch after the call (the generic path applies the
+ *                  toggle in place); world_out_dev receives t+1.  Must not alias.
+ *   stable_dev     updated in place.
+ *   actions_dev    int32 [n_envs] or NULL: one toggle_state(action) per env before the step
+ *                  (CGL/main.py:66-67); action == side*side is the no-op; other out-of-range
+ *                  values are ignored and set *err_flag_dev |= 1.
+ *   reward_out_dev int32 [n_envs] or NULL;  alive_out_dev uint32 [n_envs] or NULL. */
+int cgl_env_step(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev,
+                 uint64_t n_envs, uint32_t side, const int32_t *actions_dev, int spawn,
+                 int stable_max, int32_t *reward_out_dev, uint32_t *alive_out_dev,
+                 int *err_flag_dev, cgl_stream_t stream);
+
+/* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
+int cgl_env_step_is_fused(uint32_t side);
+
+/* Number of kernel launches one cgl_env_step call issues (for bench.py's gpu_launches). */
+int cgl_env_step_launches(uint32_t side, int has_actions);
+
+/* ---- world-only generations ("life mode": the world half of `run`, CGL/CGL.py:154-170) -----
+ * One generation of n_envs independent (rows x cols) grids.  Columns always wrap (torus).
+ * wrap_rows = 1: rows wrap (the reference's torus).  wrap_rows = 0: rows outside the array are
+ * dead -- used for row bands that carry their own ghost rows (multi-GPU halo exchange).
+ * alive_out_dev: uint32 [n_envs] popcount of the result, or NULL. */
+int cgl_life_step(const uint32_t *world_in_dev, uint32_t *world_out_dev, uint64_t n_envs,
+                  uint32_t rows, uint32_t cols, int wrap_rows, uint32_t *alive_out_dev,
+                  cgl_stream_t stream);
+
+/* `gens` generations of ONE (rows x cols) grid, ping-ponging between buf_a (input) and buf_b,
+ * `k` generations per launch kept in shared memory (temporal blocking; k = 1 streams).
+ * *result_in_a_out = 1 if the final state is in buf_a else 0.  Requires cols % 128 == 0 for
+ * the tiled kernels; other shapes fall back to cgl_life_step per generation. */
+int cgl_life_run(uint32_t *buf_a_dev, uint32_t *buf_b_dev, uint32_t rows, uint32_t cols,
+                 int wrap_rows, uint32_t gens, uint32_t k, int *result_in_a_out,
+                 cgl_stream_t stream);
+
+/* ---- reductions ----------------------------------------------------------------------------
+ * reward(): np.add.reduce(stable, dtype=int32), CGL/CGL.py:255-256 (wraps mod 2^32).
+ * alive():  np.add.reduce(world, dtype=uint32), CGL/CGL.py:259-260. */
+int cgl_reward(const int8_t *stable_dev, uint64_t n_envs, uint64_t size, int32_t *reward_out_dev,
+               cgl_stream_t stream);
+int cgl_alive(const uint32_t *world_dev, uint64_t n_envs, uint64_t words_per_env,
+              uint32_t *alive_out_dev, cgl_stream_t stream);
+/* match(): (world == other).all(), CGL/CGL.py:269-270, on packed planes.
+ * *equal_out_dev (int32) = 1 if all n_words are equal else 0. */
+int cgl_match(const uint32_t *a_dev, const uint32_t *b_dev, uint64_t n_words, int *equal_out_dev,
+              cgl_stream_t stream);
+
+/* ---- host-buffer entry point: literal replacement of sim.__step_state_gpu -----------------
+ * CGL/CGL.py:203-208: H2D world + stable, one generation, D2H world + stable, in place into
+ * the caller's numpy buffers (reference array format: uint8 / int8 [side*side]).  Synchronous.
+ * Internally packs on the device and runs the same kernels as cgl_env_step. */
+int cgl_step_state_gpu(uint8_t *world_host, int8_t *stable_host, uint32_t side, int spawn,
+                       int stable_max);
+
+/* Batched host-buffer step (used for the end-to-end bench): actions int32[n_envs] or NULL on the
+ * host; resident device state (packed world ping-pong + stable) identified by the pointers;
+ * copies actions H2D, steps, copies reward (and the observation if obs_host != NULL) D2H.
+ * All host buffers should be pinned for the copies to be asynchronous. Synchronous on return. */
+int cgl_env_step_host(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev,
+                      uint64_t n_envs, uint32_t side, const int32_t *actions_host,
+                      int32_t *actions_dev_scratch, int spawn, int stable_max,
+                      int32_t *reward_dev_scratch, int32_t *reward_host, int8_t *obs_host,
+                      cgl_stream_t stream);
+
+/* ---- CUDA IPC helpers for the row-band halo exchange over NVLink (multi-GPU life mode) ----
+ * One process per GPU; each rank exports its ghost-row buffer and maps its neighbours'. */
+int cgl_ipc_get_handle(void *dev_ptr, uint8_t handle_out[64]);
+int cgl_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out);
+int cgl_ipc_close_handle(void *dev_ptr);
+
+/* Push `n_words` from a local buffer into a peer-mapped buffer and then publish `seq` to the
+ * peer's flag word (release semantics), in one kernel; the peer waits with cgl_halo_wait. */
+int cgl_halo_push(const uint32_t *src_dev, uint32_t *peer_dst_dev, uint64_t n_words,
+                  uint32_t *peer_flag_dev, uint32_t seq, cgl_stream_t stream);
+/* Block the stream until *flag_dev >= seq (written by a peer GPU). */
+int cgl_halo_wait(const uint32_t *flag_dev, uint32_t seq, cgl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGL_B200_H */

@@ -1,0 +1,307 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (libcgl_b200.so), against
+ (a) the golden vectors recorded from the reference's own CPU step (tests/golden/), and
+ (b) the CPU oracle on the same seeded inputs, bit-exact (all arithmetic is integer).
+Nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, TRACES
+from oracle import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+API = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_api.json")))
+
+
+@pytest.fixture(scope="module")
+def cgl():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    os.environ.pop("GPU_CAPABLE", None)
+    import importlib
+    import CGL
+    return importlib.reload(CGL)
+
+
+@pytest.fixture(scope="module")
+def B(cgl):
+    from cgl_b200.batched import BatchedSim
+    return BatchedSim
+
+
+def dev_np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# (a) golden traces through the reference-facing facade
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(TRACES))
+def test_facade_replays_reference_trace(cgl, name):
+    tr = TRACES[name]
+    env = cgl.sim(state=tr.worlds[0].reshape(tr.side, tr.side), gpu=True,
+                  spawnStabilityFactor=tr.spawn, stableStabilityFactor=tr.stable_max)
+    assert np.array_equal(env.get_stable(vector=True), tr.stables[0])
+    assert env.reward() == tr.rewards[0] and env.alive() == tr.alives[0]
+    obs = env.get_stable(vector=True, shallow=True)
+    for t in range(tr.T):
+        a = tr.action(t)
+        if a is not None:
+            env.toggle_state(np.int32(a) if isinstance(a, int) else a)
+        assert env.reward() == tr.rewards_after_toggle[t], (name, t)
+        env.step()
+        assert np.array_equal(env.get_state(vector=True), tr.worlds[t + 1]), (name, t)
+        assert np.array_equal(env.get_stable(vector=True), tr.stables[t + 1]), (name, t)
+        assert obs is env.get_stable(vector=True, shallow=True)           # N1 aliasing
+        assert np.array_equal(obs, tr.stables[t + 1])
+        r, al = env.reward(), env.alive()
+        assert isinstance(r, np.int32) and isinstance(al, np.uint32)
+        assert r == tr.rewards[t + 1] and al == tr.alives[t + 1]
+    assert env.get_count() == tr.T
+
+
+def test_facade_random_start_uses_reference_rng(cgl):
+    tr = TRACES["rand64_plain"]
+    env = cgl.sim(side=64, seed=0, gpu=True, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    assert np.array_equal(env.get_state(vector=True), tr.worlds[0])
+    for t in range(10):
+        env.step()
+    assert np.array_equal(env.get_state(vector=True), tr.worlds[10])
+    assert np.array_equal(env.get_stable(vector=True), tr.stables[10])
+    assert (env.alive(), env.reward()) == (772, -691)                      # SURVEY.md 8c golden (3)
+
+
+def test_facade_api_behaviour_matches_reference(cgl):
+    w0 = np.array(API["side6_seed3_world"], np.uint8)
+    env = cgl.sim(side=6, seed=3, gpu=True)
+    assert np.array_equal(env.get_state(vector=True), w0)
+    env.toggle_state([3, 3])
+    assert (env.get_state(vector=True) != w0).sum() == 1                   # duplicates toggle once
+    env.toggle_state(36)                                                   # "do nothing"
+    assert (env.get_state(vector=True) != w0).sum() == 1
+    env.toggle_state([36])
+    for bad in (37, -1, [1, 99]):
+        with pytest.raises(ValueError):
+            env.toggle_state(bad)
+    with pytest.raises(IndexError):
+        env.toggle_state([])
+    env = cgl.sim(side=5, seed=1, gpu=True, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    g = API["getters"]
+    assert (env.get_side(), env.get_count(), env.get_seed(), env.get_state_dim(), str(env.get_state_space_dim()),
+            env.get_action_space_dim()) == (g["side"], g["count"], g["seed"], g["state_dim"], g["state_space_dim"],
+                                            g["action_space_dim"])
+    init_w, init_s = env.get_state(vector=True), env.get_stable(vector=True)
+    env.step(); env.step()
+    assert env.get_count() == API["count_after_2"]
+    env.reset()
+    assert env.get_count() == API["count_after_reset"]
+    assert np.array_equal(env.get_state(vector=True), init_w) and np.array_equal(env.get_stable(vector=True), init_s)
+    with pytest.raises(ValueError):
+        env.update_state(np.zeros(9), 3)
+    with pytest.raises(ValueError):
+        env.update_state(np.zeros(25), 4)
+    new = np.arange(25) % 2
+    env.update_state(new, 5)
+    assert np.array_equal(env.get_state(vector=True), new) and np.array_equal(env.get_stable(vector=True), init_s)
+    assert env.match(new.reshape(5, 5)) is True and env.match(1 - new) is False
+    sv = env.save()
+    assert len(sv) == 6 and [type(v).__name__ for v in sv] == API["save_types"]
+    with pytest.raises(TypeError):
+        env.load([1], np.zeros(1, np.int8), 1, 0, -1, 1)
+    with pytest.raises(ValueError):
+        env.load(np.zeros(1), np.zeros(1), 0, 0, -1, 1)
+    with pytest.raises(ValueError):
+        env.load(np.zeros(1), np.zeros(1), 1, -1, -1, 1)
+    with pytest.raises(TypeError):
+        env.load(np.zeros(1), np.zeros(1), 1, 0, -1.0, 1)
+    # save -> step -> load restores; load with another side re-allocates
+    env.step()
+    env.load(*sv)
+    assert np.array_equal(env.get_state(vector=True), sv[0]) and np.array_equal(env.get_stable(vector=True), sv[1])
+    tr = TRACES["tiny7"]
+    env.load(tr.worlds[2], tr.stables[2], 7, 2, tr.spawn, tr.stable_max)
+    a = tr.action(2)
+    env.toggle_state(a); env.step()
+    assert np.array_equal(env.get_state(vector=True), tr.worlds[3]) and np.array_equal(env.get_stable(vector=True), tr.stables[3])
+    assert env.get_state().shape == (7, 7) and env.get_stable().dtype == np.int8 and env.get_state().dtype == np.uint8
+    with pytest.raises(RuntimeError):
+        env.step(forceCPU=True)
+    with pytest.raises(ValueError):
+        cgl.sim(state=np.array([0, 2, 1, 0]), gpu=True)
+
+
+# ------------------------------------------------------------------------------------------
+# (b) batched driver vs golden envs and vs the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("side,n", [(64, 6), (128, 2)])
+def test_batched_fused_matches_golden_envs(B, side, n):
+    trs = [TRACES[f"env{side}_{e}"] for e in range(n)]
+    env = B(n, side, seed=0, spawnStabilityFactor=-2, stableStabilityFactor=2)      # env e seeded seed+e
+    assert env.fused
+    assert np.array_equal(dev_np(env.get_state()), np.stack([t.worlds[0] for t in trs]))
+    for t in range(trs[0].T):
+        acts = torch.tensor([tr.actions[t, 0] for tr in trs], dtype=torch.int32, device="cuda")
+        obs, rew, done = env.step(acts, want_alive=True)
+        assert np.array_equal(dev_np(env.get_state()), np.stack([tr.worlds[t + 1] for tr in trs]))
+        assert np.array_equal(dev_np(obs), np.stack([tr.stables[t + 1] for tr in trs]))
+        assert dev_np(rew).tolist() == [int(tr.rewards[t + 1]) for tr in trs]
+        assert dev_np(env.last_alive()).tolist() == [int(tr.alives[t + 1]) for tr in trs]
+        assert not bool(done.any())
+    env.check_actions()
+
+
+def _random_case(side, n_envs, spawn, smax, seed, steps, BatchedSim, with_actions=True):
+    rs = np.random.RandomState(seed)
+    size = side * side
+    cells = rs.randint(2, size=(n_envs, size)).astype(np.uint8)
+    st = rs.randint(-128, 128, size=(n_envs, size)).astype(np.int8)
+    env = BatchedSim(n_envs, side, spawnStabilityFactor=spawn, stableStabilityFactor=smax, states=cells)
+    env.stable.copy_(torch.from_numpy(st))
+    for _ in range(steps):
+        acts = rs.randint(size + 1, size=n_envs).astype(np.int32) if with_actions else None
+        rew_o, alv_o = oracle.step_batch(cells, st, side, acts, spawn, smax, threads=4)
+        obs, rew, _ = env.step(None if acts is None else torch.from_numpy(acts).cuda(), want_alive=True)
+        assert np.array_equal(dev_np(env.get_state()), cells), (side, "world")
+        assert np.array_equal(dev_np(obs), st), (side, "stable")
+        assert np.array_equal(dev_np(rew), rew_o) and np.array_equal(dev_np(env.last_alive()), alv_o.astype(np.int64))
+        assert np.array_equal(dev_np(env.reward()), rew_o) and np.array_equal(dev_np(env.alive()), alv_o.astype(np.int64))
+    env.check_actions()
+
+
+@pytest.mark.parametrize("side,n_envs,spawn,smax", [
+    (32, 9, -2, 2), (64, 5, -128, 127), (64, 133, -2, 2), (96, 3, 5, 2), (128, 7, -1, 1), (128, 1, 127, -128),
+    (160, 2, -2, 2), (192, 2, 0, 0), (224, 1, -3, 100), (256, 3, -2, 2)])
+def test_fused_kernel_random_states_vs_oracle(B, side, n_envs, spawn, smax):
+    """Arbitrary stability bytes (s > MAX, wrap at 127), random actions incl. the no-op, ragged batch sizes."""
+    _random_case(side, n_envs, spawn, smax, seed=side * 7 + n_envs, steps=3, BatchedSim=B)
+
+
+@pytest.mark.parametrize("side,n_envs", [(1, 4), (2, 3), (3, 5), (5, 2), (7, 33), (10, 64), (31, 3), (33, 2), (40, 9),
+                                         (100, 2), (200, 1), (288, 1)])
+def test_generic_kernels_random_states_vs_oracle(B, side, n_envs):
+    _random_case(side, n_envs, -2, 2, seed=side * 13 + n_envs, steps=3, BatchedSim=B)
+    _random_case(side, n_envs, -128, 127, seed=side, steps=2, BatchedSim=B, with_actions=False)
+
+
+def test_invalid_actions_are_flagged(B):
+    env = B(4, 64, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    before = dev_np(env.get_state()).copy()
+    env.step(torch.tensor([4096, 4097, -1, 4096], dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        env.check_actions()
+    env.check_actions()                                  # flag cleared
+    cells, st = before.copy(), oracle.initial_stable(before.reshape(-1), -2).reshape(4, -1)
+    oracle.step_batch(cells, st, 64, None, -2, 2)        # invalid actions were treated as no-ops
+    assert np.array_equal(dev_np(env.get_state()), cells)
+    env10 = B(2, 10)
+    env10.step(torch.tensor([100, 101], dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        env10.check_actions()
+
+
+def test_multi_index_toggle_matches_oracle(B):
+    rs = np.random.RandomState(5)
+    for side in (10, 64):
+        size, n = side * side, 7
+        cells = rs.randint(2, size=(n, size)).astype(np.uint8)
+        st = rs.randint(-128, 128, size=(n, size)).astype(np.int8)
+        env = B(n, side, spawnStabilityFactor=-2, stableStabilityFactor=2, states=cells)
+        env.stable.copy_(torch.from_numpy(st))
+        idx = rs.randint(size, size=(n, 4)).astype(np.int32)
+        idx[0] = [3, 3, 3, 9]; idx[1] = [size, 5, size, 5]           # duplicates + no-op padding
+        env.toggle(torch.from_numpy(idx).cuda())
+        for e in range(n):
+            valid = [int(v) for v in idx[e] if v != size]
+            oracle.toggle(cells[e], st[e], valid, -2)
+        assert np.array_equal(dev_np(env.get_state()), cells) and np.array_equal(dev_np(env.stable), st)
+        env.check_actions()
+
+
+def test_sharding_by_env_index_is_partition_invariant(B):
+    """N ranks owning [r*B/G, (r+1)*B/G) produce exactly the rows a single GPU produces."""
+    full = B(8, 64, seed=11, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    parts = [B.shard(8, 64, r, 4, seed=11, spawnStabilityFactor=-2, stableStabilityFactor=2) for r in range(4)]
+    acts = torch.randint(0, 4097, (3, 8), dtype=torch.int32, device="cuda")
+    for t in range(3):
+        _, rew, _ = full.step(acts[t])
+        for r, p in enumerate(parts):
+            _, prew, _ = p.step(acts[t, 2 * r:2 * r + 2].contiguous())
+            assert torch.equal(prew, rew[2 * r:2 * r + 2])
+            assert torch.equal(p.stable, full.stable[2 * r:2 * r + 2])
+
+
+def test_host_buffer_entry_points(B):
+    """cgl_step_state_gpu == the reference's __step_state_gpu contract; step_host == step."""
+    from cgl_b200 import native
+    lib = native.load()
+    for name in ("rand64_plain", "tiny10", "env200_0", "blinker5"):
+        tr = TRACES[name]
+        w, s = tr.worlds[0].copy(), tr.stables[0].copy()
+        for t in range(min(tr.T, 4)):
+            a = tr.action(t)
+            if a is not None:
+                oracle.toggle(w, s, a, tr.spawn)
+            native.check(lib.cgl_step_state_gpu(w.ctypes.data, s.ctypes.data, tr.side, tr.spawn, tr.stable_max))
+            assert np.array_equal(w, tr.worlds[t + 1]) and np.array_equal(s, tr.stables[t + 1]), (name, t)
+    a = B(16, 64, seed=3, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    b = B(16, 64, seed=3, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    acts_h = torch.empty(16, dtype=torch.int32).pin_memory()
+    rew_h = torch.empty(16, dtype=torch.int32).pin_memory()
+    obs_h = torch.empty((16, 4096), dtype=torch.int8).pin_memory()
+    for t in range(3):
+        acts_h.copy_(torch.randint(0, 4097, (16,), dtype=torch.int32))
+        a.step_host(acts_h, rew_h, obs_h)
+        obs, rew, _ = b.step(acts_h.cuda())
+        assert torch.equal(rew.cpu(), rew_h) and torch.equal(obs.cpu(), obs_h)
+
+
+# ------------------------------------------------------------------------------------------
+# life mode (world-only generations of large grids)
+# ------------------------------------------------------------------------------------------
+def _life_step(lib, native, win, rows, cols, wrap, n_envs=1, want_alive=True):
+    out = torch.empty_like(win)
+    alive = torch.zeros(n_envs, dtype=torch.int32, device="cuda")
+    native.check(lib.cgl_life_step(native.dptr(win), native.dptr(out), n_envs, rows, cols, wrap,
+                                   native.dptr(alive) if want_alive else None, native.current_stream()))
+    return out, alive
+
+
+def _pack(lib, native, cells, n_envs, rows, cols):
+    W = (cols + 31) // 32
+    out = torch.empty(n_envs * rows * W, dtype=torch.int32, device="cuda")
+    c = torch.from_numpy(np.ascontiguousarray(cells, np.uint8)).cuda()
+    native.check(lib.cgl_pack(native.dptr(c), native.dptr(out), n_envs, rows, cols, native.current_stream()))
+    return out
+
+
+def _unpack(lib, native, w, n_envs, rows, cols):
+    out = torch.empty(n_envs * rows * cols, dtype=torch.uint8, device="cuda")
+    native.check(lib.cgl_unpack(native.dptr(w), native.dptr(out), n_envs, rows, cols, native.current_stream()))
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("rows,cols,n_envs", [(50, 2048, 1), (131, 4096, 1), (64, 4096 + 128 * 5, 2), (300, 8192, 1),
+                                              (17, 100, 3), (9, 2176, 1)])
+@pytest.mark.parametrize("wrap", [1, 0])
+def test_life_step_vs_oracle(cgl, rows, cols, n_envs, wrap):
+    from cgl_b200 import native
+    lib = native.load()
+    rs = np.random.RandomState(rows + cols)
+    cells = rs.randint(2, size=(n_envs, rows, cols)).astype(np.uint8)
+    w = _pack(lib, native, cells, n_envs, rows, cols)
+    for g in range(3):
+        w, alive = _life_step(lib, native, w, rows, cols, wrap, n_envs)
+        for e in range(n_envs):
+            if wrap:
+                cells[e] = oracle.life(cells[e], 1, threads=4)
+            else:       # dead rows outside, torus columns == torus on a grid padded with 2 dead rows, re-killed
+                padded = np.zeros((rows + 2, cols), np.uint8)
+                padded[1:-1] = cells[e]
+                cells[e] = oracle.life(padded, 1, threads=4)[1:-1]
+        got = _unpack(lib, native, w, n_envs, rows, cols).reshape(n_envs, rows, cols)
+        assert np.array_equal(got, cells), (rows, cols, wrap, g)
+        assert (alive.cpu().numpy().astype(np.int64) & 0xFFFFFFFF).tolist() == cells.reshape(n_envs, -1).sum(1).tolist()

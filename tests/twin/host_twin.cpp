@@ -1,0 +1,135 @@
+// host_twin.cpp -- TEST INFRASTRUCTURE: compiles the product's bit logic
+// (ecen743-project-cgol_b200/csrc/cgl_bits.cuh, the very expressions the sm_100a kernels run)
+// with g++ so the CPU box can check it against the oracle before any GPU time is spent.
+// Loop structure mirrors the kernels in cgl_env.cu (generic and fused paths); it is not shipped.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../ecen743-project-cgol_b200/csrc/cgl_bits.cuh"
+
+using namespace cgl;
+
+extern "C" {
+
+void twin_pack(const uint8_t *cells, uint32_t *world, uint64_t n_envs, uint32_t rows, uint32_t cols)
+{
+    const uint32_t W = (cols + 31) / 32;
+    for (uint64_t row = 0; row < n_envs * rows; ++row)
+        for (uint32_t w = 0; w < W; ++w) {
+            uint32_t word = 0;
+            for (uint32_t j = 0; j < 32; ++j) {
+                uint32_t col = w * 32 + j;
+                if (col < cols && cells[row * cols + col] != 0) word |= 1u << j;
+            }
+            world[row * W + w] = word;
+        }
+}
+
+void twin_unpack(const uint32_t *world, uint8_t *cells, uint64_t n_envs, uint32_t rows, uint32_t cols)
+{
+    const uint32_t W = (cols + 31) / 32;
+    for (uint64_t row = 0; row < n_envs * rows; ++row)
+        for (uint32_t c = 0; c < cols; ++c) cells[row * cols + c] = (world[row * W + (c >> 5)] >> (c & 31)) & 1u;
+}
+
+// mirrors life_generic_kernel
+void twin_life_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows, uint32_t cols,
+                       int wrap_rows)
+{
+    const uint32_t W = (cols + 31) / 32;
+    const uint64_t wpe = (uint64_t)rows * W;
+    const uint32_t rbits = cols - 32 * (W - 1);
+    const uint32_t last_mask = rbits == 32 ? 0xffffffffu : ((1u << rbits) - 1u);
+    for (uint64_t e = 0; e < n_envs; ++e)
+        for (uint32_t r = 0; r < rows; ++r)
+            for (uint32_t w = 0; w < W; ++w) {
+                const uint32_t *base = in + e * wpe;
+                RowPlanes pc = load_row_planes(base + (uint64_t)r * W, w, W, rbits);
+                RowPlanes pa = {0, 0, 0}, pb = {0, 0, 0};
+                if (r > 0) pa = load_row_planes(base + (uint64_t)(r - 1) * W, w, W, rbits);
+                else if (wrap_rows) pa = load_row_planes(base + (uint64_t)(rows - 1) * W, w, W, rbits);
+                if (r + 1 < rows) pb = load_row_planes(base + (uint64_t)(r + 1) * W, w, W, rbits);
+                else if (wrap_rows) pb = load_row_planes(base, w, W, rbits);
+                uint32_t nxt = life_rule(hsum(pa.west, pa.c, pa.east), hsum(pc.west, pc.c, pc.east),
+                                         hsum(pb.west, pb.c, pb.east), pc.c);
+                if (w == W - 1) nxt &= last_mask;
+                out[e * wpe + (uint64_t)r * W + w] = nxt;
+            }
+}
+
+// mirrors stable_generic_kernel
+void twin_stable_generic(const uint32_t *prev, const uint32_t *next, int8_t *stable, uint64_t n_envs,
+                         uint32_t side, int spawn, int stable_max)
+{
+    const uint32_t W = (side + 31) / 32;
+    const uint64_t size = (uint64_t)side * side;
+    for (uint64_t e = 0; e < n_envs; ++e)
+        for (uint32_t r = 0; r < side; ++r)
+            for (uint32_t c = 0; c < side; ++c) {
+                const uint64_t widx = (e * side + r) * W + (c >> 5);
+                const bool p = (prev[widx] >> (c & 31)) & 1u, n = (next[widx] >> (c & 31)) & 1u;
+                int8_t &s = stable[e * size + (uint64_t)r * side + c];
+                s = stable_update1(s, p, n, (int8_t)spawn, (int8_t)stable_max);
+            }
+}
+
+// mirrors env_step_fused_kernel (side % 32 == 0): phases A (toggle), B (rule + nibble mix), C (LUT + SIMD)
+int twin_env_step_fused(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint64_t n_envs,
+                        uint32_t side, const int32_t *actions, int spawn, int stable_max, int32_t *reward_out,
+                        uint32_t *alive_out)
+{
+    if (side % 32) return -1;
+    const int S = (int)side, W = S / 32, WPE = S * W, SIZE = S * S, NCHUNK = SIZE / 16;
+    const uint32_t spawn4 = rep4(spawn), max4 = rep4(stable_max);
+    uint32_t lut[256][2];
+    for (uint32_t i = 0; i < 256; ++i) lut_entry(i, spawn4, lut[i][0], lut[i][1]);
+    std::vector<uint32_t> cur(WPE), mix(2 * WPE);
+    int err = 0;
+    for (uint64_t e = 0; e < n_envs; ++e) {
+        int act = -1;
+        if (actions) {
+            int a = actions[e];
+            if (a >= 0 && a < SIZE) act = a;
+            else if (a != SIZE) err = 1;
+        }
+        memcpy(cur.data(), world_in + e * WPE, WPE * 4);
+        if (act >= 0) cur[act >> 5] ^= 1u << (act & 31);
+        uint32_t pop = 0;
+        for (int i = 0; i < WPE; ++i) {
+            const int r = i / W, w = i % W;
+            const int ru = (r == 0 ? S - 1 : r - 1) * W, rc = r * W, rd = (r == S - 1 ? 0 : r + 1) * W;
+            const int wl = (w == 0 ? W - 1 : w - 1), wr = (w == W - 1 ? 0 : w + 1);
+            const uint32_t a = cur[ru + w], c = cur[rc + w], b = cur[rd + w];
+            const HSum ha = hsum(west_plane(cur[ru + wl], a), a, east_plane(a, cur[ru + wr]));
+            const HSum hc = hsum(west_plane(cur[rc + wl], c), c, east_plane(c, cur[rc + wr]));
+            const HSum hb = hsum(west_plane(cur[rd + wl], b), b, east_plane(b, cur[rd + wr]));
+            const uint32_t nxt = life_rule(ha, hc, hb, c);
+            world_out[e * WPE + i] = nxt;
+            pop += __builtin_popcount(nxt);
+            mix_nibbles(c, nxt, mix[2 * i], mix[2 * i + 1]);
+        }
+        uint32_t *sp = reinterpret_cast<uint32_t *>(stable + e * SIZE);
+        int32_t acc = 0;
+        for (int q = 0; q < NCHUNK; ++q) {
+            uint32_t s[4] = {sp[4 * q], sp[4 * q + 1], sp[4 * q + 2], sp[4 * q + 3]};
+            if (act >= 0 && q == (act >> 4)) {
+                const uint32_t m = 0xffu << ((act & 3) * 8);
+                const int k = (act >> 2) & 3;
+                s[k] = (s[k] & ~m) | (spawn4 & m);
+            }
+            const uint32_t m = mix[q];
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t idx = (m >> (8 * k)) & 0xffu;
+                s[k] = stable_update4(s[k], lut[idx][0], lut[idx][1], max4);
+                for (int b = 0; b < 4; ++b) acc += (int8_t)(s[k] >> (8 * b));
+                sp[4 * q + k] = s[k];
+            }
+        }
+        if (reward_out) reward_out[e] = acc;
+        if (alive_out) alive_out[e] = pop;
+    }
+    return err;
+}
+
+}  // extern "C"
