@@ -50,6 +50,9 @@ SIGNATURES = {
     "cgl_ipc_close_handle": (_i, [_vp]),
     "cgl_halo_push": (_i, [_vp, _vp, _u64, _vp, _u32, _vp]),
     "cgl_halo_wait": (_i, [_vp, _u32, _vp]),
+    "cgl_halo_wait_copy": (_i, [_vp, _u32, _vp, _vp, _u64, _vp]),
+    "cgl_dev_alloc": (_i, [_u64, ctypes.POINTER(_vp)]),
+    "cgl_dev_free": (_i, [_vp]),
 }
 
 _lib = None

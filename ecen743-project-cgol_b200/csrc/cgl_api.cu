@@ -42,14 +42,25 @@ __global__ void halo_push_kernel(const uint4 *__restrict__ src, uint4 *__restric
     }
 }
 
-__global__ void halo_wait_kernel(const uint32_t *flag, uint32_t seq)
+__device__ __forceinline__ void spin_until(const uint32_t *flag, uint32_t seq)
 {
     uint32_t v;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int32_t)(v - seq) >= 0) break;
-        __nanosleep(100);
+        __nanosleep(64);
     } while (true);
+}
+
+__global__ void halo_wait_kernel(const uint32_t *flag, uint32_t seq) { spin_until(flag, seq); }
+
+// Wait for the peer's strip (flag >= seq), then move it from the landing zone into the ghost rows.
+__global__ void halo_wait_copy_kernel(const uint32_t *flag, uint32_t seq, const uint4 *__restrict__ src,
+                                      uint4 *__restrict__ dst, uint64_t n_vec)
+{
+    if (threadIdx.x == 0) spin_until(flag, seq);
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
 }
 
 }  // namespace cgl
@@ -191,6 +202,31 @@ extern "C" int cgl_halo_push(const uint32_t *src, uint32_t *peer_dst, uint64_t n
                                                         reinterpret_cast<uint4 *>(peer_dst), n_words / 4,
                                                         peer_flag, seq);
     CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_halo_wait_copy(const uint32_t *flag, uint32_t seq, const uint32_t *src, uint32_t *dst,
+                                  uint64_t n_words, cgl_stream_t stream)
+{
+    CGL_REQUIRE(flag && src && dst && n_words && n_words % 4 == 0, CGL_E_BADARG,
+                "cgl_halo_wait_copy: bad argument (n_words must be a multiple of 4)");
+    halo_wait_copy_kernel<<<1, 1024, 0, as_stream(stream)>>>(flag, seq, reinterpret_cast<const uint4 *>(src),
+                                                             reinterpret_cast<uint4 *>(dst), n_words / 4);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_dev_alloc(uint64_t bytes, void **dev_ptr_out)
+{
+    CGL_REQUIRE(bytes && dev_ptr_out, CGL_E_BADARG, "cgl_dev_alloc: bad argument");
+    CGL_CUDA(cudaMalloc(dev_ptr_out, bytes));
+    CGL_CUDA(cudaMemset(*dev_ptr_out, 0, bytes));
+    return 0;
+}
+
+extern "C" int cgl_dev_free(void *dev_ptr)
+{
+    CGL_CUDA(cudaFree(dev_ptr));
     return 0;
 }
 

@@ -116,7 +116,7 @@ CGL_HD int8_t stable_update1(int8_t s, bool prev, bool next, int8_t spawn, int8_
     return 0;
 }
 
-// Interleave the nibbles of `cur` and `nxt` (32 cells) into 8 LUT-index bytes
+// Interleave the nibbles of two 32-cell planes `cur` and `nxt` into 8 bytes
 // ((cur_nibble << 4) | nxt_nibble), ordered so that out[0] serves cells 0..15 and out[1]
 // serves cells 16..31, byte k of out[h] <-> cells 16h + 4k .. 16h + 4k + 3.
 CGL_HD void mix_nibbles(uint32_t cur, uint32_t nxt, uint32_t &out_lo, uint32_t &out_hi)
@@ -131,15 +131,6 @@ CGL_HD void mix_nibbles(uint32_t cur, uint32_t nxt, uint32_t &out_lo, uint32_t &
     out_hi = ((even >> 16) & 0xffu) | (((odd >> 16) & 0xffu) << 8) | (((even >> 24) & 0xffu) << 16) |
              (((odd >> 24) & 0xffu) << 24);
 #endif
-}
-
-// LUT entry for index byte (cur_nibble << 4) | nxt_nibble:  .x = surv byte mask,
-// .y = born byte mask & SPAWN replicated.
-CGL_HD void lut_entry(uint32_t idx, uint32_t spawn4, uint32_t &surv_mask, uint32_t &born_spawn)
-{
-    uint32_t cur = idx >> 4, nxt = idx & 0xfu;
-    surv_mask = nibble_to_bytemask(cur & nxt);
-    born_spawn = nibble_to_bytemask(nxt & ~cur & 0xfu) & spawn4;
 }
 
 CGL_HD uint32_t rep4(int v) { return (uint32_t)(uint8_t)v * 0x01010101u; }

@@ -6,6 +6,8 @@
 // modulos): state is 1 bit per cell + 1 int8 per cell, the generation is bit-sliced LOP3 logic on
 // 32 cells per instruction, and the stability plane is streamed once with 128-bit accesses and
 // updated 4 cells per instruction.
+#include <stdlib.h>
+
 #include "cgl_internal.cuh"
 
 namespace cgl {
@@ -18,7 +20,7 @@ namespace cgl {
 //   phase A  world words -> shared memory (uint4, coalesced), action bit flipped on the way
 //   phase B  next generation from shared memory (9 LDS + ~12 LOP3 per 32 cells), stored to
 //            HBM; (cur,next) nibbles interleaved into one LUT-index byte per 4 cells
-//   phase C  stability stream: LDG.128 -> 4 x {LDS.64 mask LUT, byte-SIMD update, IDP.4A}
+//   phase C  stability stream: LDG.128 -> 4 x {2 conflict-free mask LDS, byte-SIMD update, IDP.4A}
 //            -> STG.128; reward reduced with REDUX + one shared atomic per warp
 // =========================================================================================
 template <int S>
@@ -32,9 +34,17 @@ struct EnvCfg {
     static constexpr int THREADS = TPE * EPC;
     static constexpr int CPT = NCHUNK / TPE;      // chunks per thread
     static constexpr int UNR = CPT < 8 ? CPT : 8; // chunks in flight per thread
-    static constexpr int SMEM = 256 * 8 + EPC * (WPE * 4 + WPE * 8) + EPC * 8;
+    // [<= 4 KB align slack][mask tables 4 KB][per env: cur WPE*4 | mix WPE*8][per env: 2 ints]
+    static constexpr int SMEM = 4096 + 4096 + EPC * (WPE * 4 + WPE * 8) + EPC * 8;
     static_assert(S % 32 == 0 && NCHUNK % TPE == 0 && WPE % 4 == 0, "unsupported side");
 };
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
 
 template <int S>
 __global__ void __launch_bounds__(EnvCfg<S>::THREADS)
@@ -45,13 +55,20 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                       int *__restrict__ err_flag)
 {
     using C = EnvCfg<S>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2 *lut = reinterpret_cast<uint2 *>(smem_raw);
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // Mask tables, one copy per lane so that a lookup never bank-conflicts:
+    //   word (nib*64 + which*32 + lane): which 0 = byte mask of `nib`, which 1 = that mask & SPAWN.
+    // The table base is aligned to 4 KB so that a lookup address is ONE byte-permute:
+    //   addr = TB | nib << 8 | which << 7 | lane << 2.
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+    const uint32_t tb = (sbase + 4095u) & ~4095u;
+    unsigned char *smem_raw = smem_dyn + (tb - sbase);
+    uint32_t *tables = reinterpret_cast<uint32_t *>(smem_raw);
     const int g = threadIdx.x / C::TPE;           // env slot in this CTA
     const int t = threadIdx.x % C::TPE;
-    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw + 2048) + g * (C::WPE * 3);
+    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw + 4096) + g * (C::WPE * 3);
     uint32_t *mix = cur + C::WPE;                 // 2 words per world word
-    int *red = reinterpret_cast<int *>(smem_raw + 2048 + C::EPC * C::WPE * 12) + g * 2;
+    int *red = reinterpret_cast<int *>(smem_raw + 4096 + C::EPC * C::WPE * 12) + g * 2;
 
     const uint32_t e = blockIdx.x * C::EPC + g;
     const bool active = e < n_envs;
@@ -64,10 +81,9 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         for (int u = 0; u < C::UNR; ++u) sreg[u] = sp[t + u * C::TPE];
     }
 
-    for (int i = threadIdx.x; i < 256; i += C::THREADS) {
-        uint32_t sm, bs;
-        lut_entry((uint32_t)i, spawn4, sm, bs);
-        lut[i] = make_uint2(sm, bs);
+    for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
+        const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
+        tables[i] = (i & 32) ? (m & spawn4) : m;
     }
     if (t == 0) { red[0] = 0; red[1] = 0; }
 
@@ -115,8 +131,8 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             const uint32_t nxt = life_rule(ha, hc, hb, c);
             wo[i] = nxt;
             pop += __popc(nxt);
-            uint32_t lo, hi;
-            mix_nibbles(c, nxt, lo, hi);
+            uint32_t lo, hi;                      // byte per 4 cells: born nibble << 4 | surv nibble
+            mix_nibbles(nxt & ~c, nxt & c, lo, hi);
             reinterpret_cast<uint2 *>(mix)[i] = make_uint2(lo, hi);
         }
     }
@@ -125,9 +141,14 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     // ---- phase C: stability stream + reward -------------------------------------------------
     int acc = 0;
     if (active) {
-        const int act_chunk = act >> 4;                      // -1 when no action
+        // stable[action] = spawn before the update (CGL.py:326): chunk act>>4 is chunk number
+        // act_u of thread act_t -- an env-uniform test per chunk, the patch itself runs once.
+        const int act_u = act >= 0 ? (act >> 4) / C::TPE : -1;
+        const int act_t = (act >> 4) % C::TPE;
         const int act_sub = (act >> 2) & 3;
         const uint32_t act_mask = 0xffu << ((act & 3) * 8);
+        const uint32_t tbn = ((tb >> 8) & 0xffu) * 0x01010101u;   // table-base byte under every nibble
+        const uint32_t lane_s = (threadIdx.x & 31) * 4, lane_b = lane_s + 128;
 #pragma unroll
         for (int b0 = 0; b0 < C::CPT; b0 += C::UNR) {
             if (b0 > 0) {
@@ -139,17 +160,25 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             for (int u = 0; u < C::UNR; ++u) {
                 if (b0 + u >= C::CPT) continue;
                 const int q = t + (b0 + u) * C::TPE;
-                uint32_t s[4] = {sreg[u].x, sreg[u].y, sreg[u].z, sreg[u].w};
-                if (q == act_chunk) {                        // stable[action] = spawn (CGL.py:326)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k == act_sub) s[k] = (s[k] & ~act_mask) | (spawn4 & act_mask);
+                if (act_u == b0 + u) {
+                    if (t == act_t) {
+                        const uint32_t keep = ~act_mask, put = spawn4 & act_mask;
+                        if (act_sub == 0) sreg[u].x = (sreg[u].x & keep) | put;
+                        else if (act_sub == 1) sreg[u].y = (sreg[u].y & keep) | put;
+                        else if (act_sub == 2) sreg[u].z = (sreg[u].z & keep) | put;
+                        else sreg[u].w = (sreg[u].w & keep) | put;
+                    }
                 }
+                uint32_t s[4] = {sreg[u].x, sreg[u].y, sreg[u].z, sreg[u].w};
                 const uint32_t m = mix[q];
+                const uint32_t sv = (m & 0x0f0f0f0fu) | tbn;
+                const uint32_t bn = ((m >> 4) & 0x0f0f0f0fu) | tbn;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint2 l = lut[(m >> (8 * k)) & 0xffu];
-                    s[k] = stable_update4(s[k], l.x, l.y, max4);
+                    // address bytes: [lane*4 (+128 for the born table), TBhi | nibble, 0, 0]
+                    const uint32_t surv_mask = lds_u32(__byte_perm(sv, lane_s, 0x5504 + 16 * k));
+                    const uint32_t born_spawn = lds_u32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
+                    s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
                     acc = __dp4a((int)s[k], 0x01010101, acc);
                 }
                 sp[q] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -178,7 +207,14 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
 {
     using C = EnvCfg<S>;
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
-    env_step_fused_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(
+    static int pad = -1;                        // tuning knob: extra dynamic smem limits CTAs/SM
+    if (pad < 0) {
+        const char *v = getenv("CGL_ENV_SMEM_PAD");
+        pad = v ? atoi(v) : 0;
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::SMEM + pad));
+    }
+    env_step_fused_kernel<S><<<grid, C::THREADS, C::SMEM + pad, st>>>(
         win, wout, stable, (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive,
         err);
     CGL_LAUNCH_CHECK();
@@ -447,6 +483,32 @@ extern "C" int cgl_toggle(uint32_t *world, int8_t *stable, uint64_t n_envs, uint
 
 extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,
                              uint32_t cols, int wrap_rows, uint32_t *alive_out, cgl_stream_t stream);
+extern "C" int cgl_env_step_tma(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
+                                const int32_t *actions, int spawn, int stable_max, int32_t *reward,
+                                uint32_t *alive, int *err, cgl_stream_t stream, int threads);
+
+// Tuning knobs (environment, read once): CGL_ENV_IMPL = "fused" (default) | "tma";
+// CGL_ENV_TMA_THREADS = 128 | 256 (default).  Measured on B200 (tools/sweep_env.py, profiles/):
+// the per-env fused kernel streams at 98-99 % of the HBM roofline once >= ~14 waves of CTAs are
+// in flight; the persistent bulk-copy kernel currently reaches 91 %, so it stays opt-in.
+static int env_impl_is_tma()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CGL_ENV_IMPL");
+        v = (e && e[0] == 't') ? 1 : 0;
+    }
+    return v;
+}
+static int env_tma_threads()
+{
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("CGL_ENV_TMA_THREADS");
+        v = (e && atoi(e) == 128) ? 128 : 256;
+    }
+    return v;
+}
 
 extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             uint32_t side, const int32_t *actions, int spawn, int stable_max,
@@ -456,6 +518,11 @@ extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint6
     CGL_REQUIRE(win != wout, CGL_E_BADARG, "cgl_env_step: world_in and world_out must not alias");
     CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step: n_envs too large");
     cudaStream_t st = as_stream(stream);
+    if (env_impl_is_tma() && (side == 32 || side == 64 || side == 128)) {
+        const int rc = cgl_env_step_tma(win, wout, stable, n_envs, side, actions, spawn, stable_max, reward,
+                                        alive, err, stream, env_tma_threads());
+        if (rc != -100) return rc;
+    }
     if (cgl_env_step_is_fused(side)) {
 #define CGL_CASE(S)                                                                               \
     case S:                                                                                       \

@@ -16,42 +16,65 @@ namespace cgl {
 struct RowRaw { uint4 v; uint32_t halo; };
 struct RowSums { HSum h[4]; uint4 c; };
 
-// Load one row segment of this lane (all zero for a dead row outside an open band).
-__device__ __forceinline__ RowRaw load_row_raw(const uint32_t *__restrict__ grid, int64_t r,
-                                               uint32_t rows, uint32_t W, int wrap_rows,
-                                               uint32_t c4, uint32_t hidx, bool valid, bool edge)
+// Per-lane constants of a strip walk.
+struct Lane {
+    const uint32_t *gin;      // grid base of this env
+    uint32_t rows, W;
+    int wrap_rows;
+    uint32_t c4, hidx;        // uint4 column of this lane, halo word index (edge lanes)
+    bool valid, edge, edge_l, edge_r;
+};
+
+// Load this lane's segment of row r (any integer; rows outside [0, rows) wrap or are dead).
+// Straight-line code: the row index is fixed up with selects and the loads are predicated.
+__device__ __forceinline__ RowRaw load_row_raw(const Lane &L, int r)
 {
+    const int rows = (int)L.rows;
+    const bool outside = (r < 0) | (r >= rows);
+    const int rw = r < 0 ? r + rows : (r >= rows ? r - rows : r);
+    const bool live = !outside | (L.wrap_rows != 0);
+    const uint32_t *row = L.gin + (uint64_t)(uint32_t)rw * L.W;
     RowRaw o;
     o.v = make_uint4(0, 0, 0, 0);
     o.halo = 0;
-    if (r < 0 || r >= (int64_t)rows) {
-        if (!wrap_rows) return o;
-        r = r < 0 ? r + rows : r - rows;
-    }
-    const uint32_t *row = grid + (uint64_t)r * W;
-    if (valid) o.v = __ldg(reinterpret_cast<const uint4 *>(row) + c4);
-    if (edge) o.halo = __ldg(row + hidx);
+    if (L.valid && live) o.v = __ldg(reinterpret_cast<const uint4 *>(row) + L.c4);
+    if (L.edge && live) o.halo = __ldg(row + L.hidx);
     return o;
 }
 
-__device__ __forceinline__ RowSums row_sums(const RowRaw &raw, bool edge_l, bool edge_r)
+__device__ __forceinline__ void row_sums(RowSums &s, const RowRaw &raw, const Lane &L)
 {
     uint32_t left = __shfl_up_sync(0xffffffffu, raw.v.w, 1);
     uint32_t right = __shfl_down_sync(0xffffffffu, raw.v.x, 1);
-    if (edge_l) left = raw.halo;
-    if (edge_r) right = raw.halo;
-    RowSums s;
+    left = L.edge_l ? raw.halo : left;
+    right = L.edge_r ? raw.halo : right;
     s.c = raw.v;
     s.h[0] = hsum(west_plane(left, raw.v.x), raw.v.x, east_plane(raw.v.x, raw.v.y));
     s.h[1] = hsum(west_plane(raw.v.x, raw.v.y), raw.v.y, east_plane(raw.v.y, raw.v.z));
     s.h[2] = hsum(west_plane(raw.v.y, raw.v.z), raw.v.z, east_plane(raw.v.z, raw.v.w));
     s.h[3] = hsum(west_plane(raw.v.z, raw.v.w), raw.v.w, east_plane(raw.v.w, right));
-    return s;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void emit_row(const RowSums &up, const RowSums &mid, const RowSums &dn,
+                                         uint32_t *__restrict__ gout, const Lane &L, int r, unsigned &pop)
+{
+    uint4 o;
+    o.x = life_rule(up.h[0], mid.h[0], dn.h[0], mid.c.x);
+    o.y = life_rule(up.h[1], mid.h[1], dn.h[1], mid.c.y);
+    o.z = life_rule(up.h[2], mid.h[2], dn.h[2], mid.c.z);
+    o.w = life_rule(up.h[3], mid.h[3], dn.h[3], mid.c.w);
+    if (L.valid && r < (int)L.rows)
+        reinterpret_cast<uint4 *>(gout + (uint64_t)(uint32_t)r * L.W)[L.c4] = o;
+    if (COUNT && r < (int)L.rows) pop += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
 }
 
 constexpr int LIFE_ROWS_THREADS = 128;   // 4 warps = 4 horizontally adjacent column groups
-constexpr int LIFE_ROWS_PF = 4;          // rows loaded ahead per thread
+constexpr int LIFE_ROWS_PF = 6;          // rows loaded ahead per thread; multiple of 3 (window rotation)
 
+// rpt must be a multiple of LIFE_ROWS_PF; strips may run past `rows` (loads wrap / are dead,
+// stores are predicated), so the loop body is branch-free and the 3-row window of partial sums
+// rotates through three register sets A, B, C without moves.
 template <bool COUNT>
 __global__ void __launch_bounds__(LIFE_ROWS_THREADS)
 life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_envs,
@@ -59,56 +82,45 @@ life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
                  uint32_t n_rblocks, uint32_t *__restrict__ alive_out)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp = (uint64_t)blockIdx.x * (LIFE_ROWS_THREADS / 32) + (threadIdx.x >> 5);
-    const uint32_t cg = (uint32_t)(warp % n_cgroups);
-    const uint64_t tmp = warp / n_cgroups;
-    const uint32_t rb = (uint32_t)(tmp % n_rblocks);
-    const uint64_t e = tmp / n_rblocks;
+    const uint32_t warp = blockIdx.x * (LIFE_ROWS_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t cg = warp % n_cgroups;
+    const uint32_t tmp = warp / n_cgroups;
+    const uint32_t rb = tmp % n_rblocks;
+    const uint32_t e = tmp / n_rblocks;
     if (e >= n_envs) return;                                   // warp-uniform
 
+    Lane L;
     const uint32_t W4 = W >> 2;
-    const uint32_t c4 = cg * 32 + lane;
-    const bool valid = c4 < W4;
-    const bool edge_l = lane == 0;
-    const bool edge_r = valid && (lane == 31 || c4 == W4 - 1);
-    const uint32_t hidx = edge_l ? (c4 == 0 ? W - 1 : 4 * c4 - 1) : (c4 == W4 - 1 ? 0 : 4 * c4 + 4);
-    const bool edge = valid && (edge_l || edge_r);
-    const uint32_t *gin = in + e * (uint64_t)rows * W;
-    uint32_t *gout = out + e * (uint64_t)rows * W;
+    L.rows = rows; L.W = W; L.wrap_rows = wrap_rows;
+    L.c4 = cg * 32 + lane;
+    L.valid = L.c4 < W4;
+    L.edge_l = lane == 0;
+    L.edge_r = L.valid && (lane == 31 || L.c4 == W4 - 1);
+    L.hidx = L.edge_l ? (L.c4 == 0 ? W - 1 : 4 * L.c4 - 1) : (L.c4 == W4 - 1 ? 0 : 4 * L.c4 + 4);
+    L.edge = L.valid && (L.edge_l || L.edge_r);
+    L.gin = in + (uint64_t)e * rows * W;
+    uint32_t *gout = out + (uint64_t)e * rows * W;
 
-    const int64_t r0 = (int64_t)rb * rpt;
-    const int64_t r1 = (r0 + rpt < (int64_t)rows) ? r0 + rpt : (int64_t)rows;
-
-    RowSums up = row_sums(load_row_raw(gin, r0 - 1, rows, W, wrap_rows, c4, hidx, valid, edge), edge_l, edge_r);
-    RowSums mid = row_sums(load_row_raw(gin, r0, rows, W, wrap_rows, c4, hidx, valid, edge), edge_l, edge_r);
+    const int r0 = (int)(rb * rpt);
+    const int r1 = r0 + (int)rpt;
+    RowSums A, B, C;
+    row_sums(A, load_row_raw(L, r0 - 1), L);
+    row_sums(B, load_row_raw(L, r0), L);
     unsigned pop = 0;
 
-    for (int64_t r = r0; r < r1; r += LIFE_ROWS_PF) {
+    for (int r = r0; r < r1; r += LIFE_ROWS_PF) {
         RowRaw raw[LIFE_ROWS_PF];
 #pragma unroll
-        for (int u = 0; u < LIFE_ROWS_PF; ++u) {
-            raw[u].v = make_uint4(0, 0, 0, 0);
-            raw[u].halo = 0;
-            if (r + u < r1) raw[u] = load_row_raw(gin, r + u + 1, rows, W, wrap_rows, c4, hidx, valid, edge);
-        }
+        for (int u = 0; u < LIFE_ROWS_PF; ++u) raw[u] = load_row_raw(L, r + u + 1);
 #pragma unroll
-        for (int u = 0; u < LIFE_ROWS_PF; ++u) {
-            if (r + u < r1) {                                   // warp-uniform
-                const RowSums dn = row_sums(raw[u], edge_l, edge_r);
-                uint4 o;
-                o.x = life_rule(up.h[0], mid.h[0], dn.h[0], mid.c.x);
-                o.y = life_rule(up.h[1], mid.h[1], dn.h[1], mid.c.y);
-                o.z = life_rule(up.h[2], mid.h[2], dn.h[2], mid.c.z);
-                o.w = life_rule(up.h[3], mid.h[3], dn.h[3], mid.c.w);
-                if (valid) reinterpret_cast<uint4 *>(gout + (uint64_t)(r + u) * W)[c4] = o;
-                if (COUNT) pop += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
-                up = mid;
-                mid = dn;
-            }
+        for (int u = 0; u < LIFE_ROWS_PF; u += 3) {
+            row_sums(C, raw[u], L);     emit_row<COUNT>(A, B, C, gout, L, r + u, pop);
+            row_sums(A, raw[u + 1], L); emit_row<COUNT>(B, C, A, gout, L, r + u + 1, pop);
+            row_sums(B, raw[u + 2], L); emit_row<COUNT>(C, A, B, gout, L, r + u + 2, pop);
         }
     }
     if (COUNT) {
-        if (!valid) pop = 0;
+        if (!L.valid) pop = 0;
         pop = __reduce_add_sync(0xffffffffu, pop);
         if (lane == 0 && pop) atomicAdd(alive_out + e, pop);
     }
@@ -117,10 +129,10 @@ life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
 static uint32_t pick_rows_per_strip(uint64_t n_envs, uint32_t rows, uint32_t n_cgroups)
 {
     // aim for >= 8 strips per resident warp slot (148 SMs x 16 warps) to keep the tail small,
-    // but never fewer than 16 rows per strip (2 halo rows are re-read per strip).
+    // but never fewer than 12 rows per strip (2 halo rows are re-read per strip).
     const uint64_t want = (uint64_t)sm_count() * 16 * 8;
-    uint64_t rpt = 128;
-    while (rpt > 16 && n_envs * n_cgroups * ((rows + rpt - 1) / rpt) < want) rpt >>= 1;
+    uint64_t rpt = 96;                                   // multiples of LIFE_ROWS_PF
+    while (rpt > 12 && n_envs * n_cgroups * ((rows + rpt - 1) / rpt) < want) rpt >>= 1;
     return (uint32_t)rpt;
 }
 
@@ -146,7 +158,7 @@ extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs,
     const uint32_t n_rblocks = (rows + rpt - 1) / rpt;
     const uint64_t warps = n_envs * n_cgroups * n_rblocks;
     const uint64_t blocks = (warps + (LIFE_ROWS_THREADS / 32) - 1) / (LIFE_ROWS_THREADS / 32);
-    CGL_REQUIRE(blocks < (1ull << 31), CGL_E_BADARG, "cgl_life_step: grid too large");
+    CGL_REQUIRE(blocks < (1ull << 31) && warps < (1ull << 32) && rows < (1u << 30), CGL_E_BADARG, "cgl_life_step: grid too large");
     if (alive_out != nullptr) {
         CGL_CUDA(cudaMemsetAsync(alive_out, 0, n_envs * sizeof(uint32_t), st));
         life_rows_kernel<true><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(

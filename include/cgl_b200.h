@@ -149,6 +149,13 @@ int cgl_halo_push(const uint32_t *src_dev, uint32_t *peer_dst_dev, uint64_t n_wo
                   uint32_t *peer_flag_dev, uint32_t seq, cgl_stream_t stream);
 /* Block the stream until *flag_dev >= seq (written by a peer GPU). */
 int cgl_halo_wait(const uint32_t *flag_dev, uint32_t seq, cgl_stream_t stream);
+/* Same wait, then copy n_words from the landing zone `src_dev` into the ghost rows `dst_dev`. */
+int cgl_halo_wait_copy(const uint32_t *flag_dev, uint32_t seq, const uint32_t *src_dev, uint32_t *dst_dev,
+                       uint64_t n_words, cgl_stream_t stream);
+/* Plain cudaMalloc'ed (zero-filled) device memory: IPC handles need whole allocations, which
+ * a caching allocator's sub-blocks are not. */
+int cgl_dev_alloc(uint64_t bytes, void **dev_ptr_out);
+int cgl_dev_free(void *dev_ptr);
 
 #ifdef __cplusplus
 }

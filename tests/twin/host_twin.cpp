@@ -82,8 +82,8 @@ int twin_env_step_fused(const uint32_t *world_in, uint32_t *world_out, int8_t *s
     if (side % 32) return -1;
     const int S = (int)side, W = S / 32, WPE = S * W, SIZE = S * S, NCHUNK = SIZE / 16;
     const uint32_t spawn4 = rep4(spawn), max4 = rep4(stable_max);
-    uint32_t lut[256][2];
-    for (uint32_t i = 0; i < 256; ++i) lut_entry(i, spawn4, lut[i][0], lut[i][1]);
+    uint32_t table[16][2];                       // [nibble][0] = byte mask, [1] = mask & SPAWN
+    for (uint32_t i = 0; i < 16; ++i) { table[i][0] = nibble_to_bytemask(i); table[i][1] = table[i][0] & spawn4; }
     std::vector<uint32_t> cur(WPE), mix(2 * WPE);
     int err = 0;
     for (uint64_t e = 0; e < n_envs; ++e) {
@@ -107,7 +107,7 @@ int twin_env_step_fused(const uint32_t *world_in, uint32_t *world_out, int8_t *s
             const uint32_t nxt = life_rule(ha, hc, hb, c);
             world_out[e * WPE + i] = nxt;
             pop += __builtin_popcount(nxt);
-            mix_nibbles(c, nxt, mix[2 * i], mix[2 * i + 1]);
+            mix_nibbles(nxt & ~c, nxt & c, mix[2 * i], mix[2 * i + 1]);
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(stable + e * SIZE);
         int32_t acc = 0;
@@ -120,8 +120,8 @@ int twin_env_step_fused(const uint32_t *world_in, uint32_t *world_out, int8_t *s
             }
             const uint32_t m = mix[q];
             for (int k = 0; k < 4; ++k) {
-                const uint32_t idx = (m >> (8 * k)) & 0xffu;
-                s[k] = stable_update4(s[k], lut[idx][0], lut[idx][1], max4);
+                const uint32_t sv = (m >> (8 * k)) & 0xfu, bn = (m >> (8 * k + 4)) & 0xfu;
+                s[k] = stable_update4(s[k], table[sv][0], table[bn][1], max4);
                 for (int b = 0; b < 4; ++b) acc += (int8_t)(s[k] >> (8 * b));
                 sp[4 * q + k] = s[k];
             }
