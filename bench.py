@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -179,10 +179,12 @@ def time_steps(torch, fn, steps, barrier):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=4, help="rotating env batches (working set > L2)")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="how the K timed steps are launched: CUDA-graph replay (default) or one ctypes call per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3/C4/C5 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -232,17 +234,54 @@ def main():
 
     for i in range(W):
         step(i)
-    launches0 = sum(s.launches for s in sims)
+    # Launch-bound inner loop -> CUDA graph: one graph = 2R consecutive steps (every replica stepped
+    # twice, so the ping-pong planes are back in place); K steps = K // 2R replays + eager remainder.
+    cycle = 2 * R
+    graph = None
+    if args.launch == "graph":
+        side_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side_stream):
+            for i in range(cycle):
+                step(i)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side_stream):
+                for i in range(cycle):
+                    step(i)
+        graph.replay()
+        torch.cuda.synchronize()
+    per_step_launches = sims[0]._lib.cgl_env_step_launches(SIDE, 1)
+
+    def timed_region():
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done = 0
+        if graph is not None:
+            for _ in range(K // cycle):
+                graph.replay()
+            done = (K // cycle) * cycle
+        for i in range(done, K):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return e0.elapsed_time(e1) / 1e3
+
+    # clocks are sampled from here until the last timing of this workload (headline region, then
+    # the eager and L2-resident variants of the same K steps) so that short regions still get samples
     sampler = ClockSampler(local).start() if rank == 0 else None
-    dt = max_over_ranks(time_steps(torch, step, K, barrier))
-    clocks = sampler.stop() if sampler else None
-    gpu_launches = sum(s.launches for s in sims) - launches0
+    dt = max_over_ranks(timed_region())
+    gpu_launches = K * per_step_launches
+    dt_eager = max_over_ranks(time_steps(torch, step, K, barrier))
     cells_per_step = B * size * world
     value = cells_per_step * K / dt / 1e9
     ms_per_step = dt / K * 1e3
 
     # L2-resident variant (one replica, 80 MiB working set inside the 126 MB L2) -- reported, not the headline
     dt_l2 = max_over_ranks(time_steps(torch, lambda i: sims[0].step(actions[i % n_act]), K, barrier))
+    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the host-buffer C-ABI call (actions H2D, reward D2H every step) ----
     e2e = None
@@ -301,6 +340,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, R),
                 "env_steps_per_s": B * world * K / dt, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roofline, "cpu_baseline": cpu, "l2_resident_value": cells_per_step * K / dt_l2 / 1e9,
+                "launch": args.launch, "eager_value": cells_per_step * K / dt_eager / 1e9,
                 "extras": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -328,26 +368,40 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
                                   "working_set_mib_per_gpu": sim.n_envs * side * side * 1.25 / 2 ** 20}
     del sim, acts
     torch.cuda.empty_cache()
+    # C4: 65536^2 torus, row bands over the ranks, k = 8 generations per launch / per halo exchange
+    from cgl_b200.bands import RowBandLife
+    n, k, gens = 65536, 8, 200
+    band = RowBandLife(n, n, k=k, rank=rank, world_size=world, device=dev)
+    band.randomize(1)
+    band.run(2 * k)
+    dt = max_over_ranks(time_steps(torch, lambda i: band.run(gens), 1, barrier))
+    out["c4_life_65536_bands"] = {"gcups": n * n * gens / dt / 1e9, "ms_per_gen": dt / gens * 1e3, "k": k, "gens": gens,
+                                  "exchange": band.exchange, "scaling": "strong", "alive": band.alive(),
+                                  "hbm_frac_algorithmic": BYTES_PER_CELL_LIFE * n * n / world / (dt / gens) / 1e9 / peak}
+    band.close()
+    del band
+    torch.cuda.empty_cache()
     if world == 1:
-        # C4 / C5: single large grids, life mode, one GPU (row-band multi-GPU runs: see bench_bands.py)
-        for name, n in (("c4_life_65536", 65536), ("c5_life_32768", 32768)):
-            words = n * (n // 32)
-            a = torch.randint(-2 ** 31, 2 ** 31 - 1, (words,), dtype=torch.int32, device=dev)
-            b = torch.empty_like(a)
-            st = native.current_stream()
-            bufs = [a, b]
+        # C5: 32768^2 torus, sweep of the temporal-blocking depth k on one GPU
+        n = 32768
+        words = n * (n // 32)
+        a = torch.randint(-2 ** 31, 2 ** 31 - 1, (words,), dtype=torch.int32, device=dev)
+        b = torch.empty_like(a)
+        res = native.ctypes.c_int(0)
+        sweep = {}
+        for k in (1, 2, 4, 8, 16):
+            g = 48
 
-            def gen(i):
-                native.check(lib.cgl_life_step(native.dptr(bufs[i & 1]), native.dptr(bufs[(i + 1) & 1]), 1, n, n, 1,
-                                               None, st))
-            for i in range(4):
-                gen(i)
-            k = 40
-            dt = time_steps(torch, gen, k, barrier)
-            out[name] = {"gcups": n * n * k / dt / 1e9, "ms_per_gen": dt / k * 1e3, "k": 1,
-                         "hbm_frac": BYTES_PER_CELL_LIFE * n * n / (dt / k) / 1e9 / peak}
-            del a, b, bufs
-            torch.cuda.empty_cache()
+            def run(_i):
+                native.check(lib.cgl_life_run(native.dptr(a), native.dptr(b), n, n, 1, g, k, native.ctypes.byref(res),
+                                              native.current_stream()))
+            run(0)
+            dt = time_steps(torch, run, 2, barrier) / 2
+            sweep[f"k{k}"] = {"gcups": n * n * g / dt / 1e9, "us_per_gen": dt / g * 1e6,
+                              "hbm_frac_algorithmic": BYTES_PER_CELL_LIFE * n * n / (dt / g) / 1e9 / peak}
+        out["c5_life_32768_k_sweep"] = sweep
+        del a, b
+        torch.cuda.empty_cache()
     return out
 
 

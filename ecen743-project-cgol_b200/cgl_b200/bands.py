@@ -29,10 +29,22 @@ import torch
 from . import native
 
 
-def _life_step(lib, src, dst, rows, cols, wrap_rows, stream):
-    """One generation src -> dst through the C ABI (tests may monkeypatch this for CPU runs)."""
-    native.check(lib.cgl_life_step(native.dptr(src), native.dptr(dst), 1, rows, cols, wrap_rows, None, stream),
-                 "cgl_life_step")
+def _life_block(lib, a, b, rows, cols, wrap_rows, gens, k, stream) -> bool:
+    """`gens` generations starting from buffer `a`, ping-ponging with `b`, k generations per launch
+    (temporal blocking, cgl_life_run).  Returns True if the result is in `a`.
+    Tests monkeypatch this for CPU runs."""
+    res = ctypes.c_int(-1)
+    native.check(lib.cgl_life_run(native.dptr(a), native.dptr(b), rows, cols, wrap_rows, gens, k,
+                                  ctypes.byref(res), stream), "cgl_life_run")
+    return res.value == 1
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 class RowBandLife:
@@ -178,20 +190,21 @@ class RowBandLife:
     def run(self, gens: int) -> None:
         """Advance `gens` generations (blocks of k generations between exchanges)."""
         lib, st = self.lib, self._stream()
+        if self.G == 1:                      # plain torus: one call, k generations per launch
+            with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
+                if not _life_block(lib, self._a, self._b, self.band_rows, self.cols, 1, gens, self.k, st):
+                    self._a, self._b = self._b, self._a
+            self.launches += -(-gens // self.k)
+            self.generation += gens
+            return
         done = 0
         while done < gens:
             kb = min(self.k, gens - done)
-            if self.G == 1:
-                for _ in range(kb):
-                    _life_step(lib, self._a, self._b, self.band_rows, self.cols, 1, st)
+            self._exchange()
+            with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
+                if not _life_block(lib, self._a, self._b, self.buf_rows, self.cols, 0, kb, kb, st):
                     self._a, self._b = self._b, self._a
-                self.launches += kb
-            else:
-                self._exchange()
-                for _ in range(kb):
-                    _life_step(lib, self._a, self._b, self.buf_rows, self.cols, 0, st)
-                    self._a, self._b = self._b, self._a
-                self.launches += kb
+            self.launches += 1
             done += kb
             self.generation += kb
 
@@ -251,9 +264,7 @@ class LocalBands:
                 b._a[0:b.k * b.W] = bots[up]
                 b._a[(b.ghost + b.band_rows) * b.W:(b.ghost + b.band_rows + b.k) * b.W] = tops[down]
             for b in self.bands:
-                st = b._stream()
-                for _ in range(kb):
-                    _life_step(b.lib, b._a, b._b, b.buf_rows, b.cols, 0, st)
+                if not _life_block(b.lib, b._a, b._b, b.buf_rows, b.cols, 0, kb, kb, b._stream()):
                     b._a, b._b = b._b, b._a
                 b.generation += kb
             done += kb

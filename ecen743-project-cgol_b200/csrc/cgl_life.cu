@@ -9,6 +9,8 @@
 // down RPT rows keeping a 3-row window of horizontal partial sums in registers; horizontal
 // neighbours come from the adjacent lanes by warp shuffle, the two warp-edge lanes load one halo
 // word.  Per 32 cells: 2 SHF + 4 LOP3 (row sums, reused by 3 output rows) + 6 LOP3 (rule).
+#include <stdlib.h>
+
 #include "cgl_internal.cuh"
 
 namespace cgl {
@@ -22,7 +24,7 @@ struct Lane {
     uint32_t rows, W;
     int wrap_rows;
     uint32_t c4, hidx;        // uint4 column of this lane, halo word index (edge lanes)
-    bool valid, edge, edge_l, edge_r;
+    bool valid, store, edge, edge_l, edge_r;
 };
 
 // Load this lane's segment of row r (any integer; rows outside [0, rows) wrap or are dead).
@@ -64,18 +66,19 @@ __device__ __forceinline__ void emit_row(const RowSums &up, const RowSums &mid, 
     o.y = life_rule(up.h[1], mid.h[1], dn.h[1], mid.c.y);
     o.z = life_rule(up.h[2], mid.h[2], dn.h[2], mid.c.z);
     o.w = life_rule(up.h[3], mid.h[3], dn.h[3], mid.c.w);
-    if (L.valid && r < (int)L.rows)
+    if (L.store && r < (int)L.rows)
         reinterpret_cast<uint4 *>(gout + (uint64_t)(uint32_t)r * L.W)[L.c4] = o;
     if (COUNT && r < (int)L.rows) pop += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
 }
 
 constexpr int LIFE_ROWS_THREADS = 128;   // 4 warps = 4 horizontally adjacent column groups
-constexpr int LIFE_ROWS_PF = 6;          // rows loaded ahead per thread; multiple of 3 (window rotation)
 
-// rpt must be a multiple of LIFE_ROWS_PF; strips may run past `rows` (loads wrap / are dead,
-// stores are predicated), so the loop body is branch-free and the 3-row window of partial sums
-// rotates through three register sets A, B, C without moves.
-template <bool COUNT>
+// rpt must be a multiple of PF (PF a multiple of 3); strips may run past `rows` (loads wrap / are
+// dead, stores are predicated), so the loop body is branch-free and the 3-row window of partial
+// sums rotates through three register sets A, B, C without moves.  The rows of trip i+1 are loaded
+// (software pipelining) before trip i is computed, which keeps PF 16-byte loads per thread in
+// flight whatever the instruction scheduler does inside a trip.
+template <bool COUNT, int PF>
 __global__ void __launch_bounds__(LIFE_ROWS_THREADS)
 life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_envs,
                  uint32_t rows, uint32_t W, uint32_t rpt, int wrap_rows, uint32_t n_cgroups,
@@ -86,14 +89,17 @@ life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
     const uint32_t cg = warp % n_cgroups;
     const uint32_t tmp = warp / n_cgroups;
     const uint32_t rb = tmp % n_rblocks;
-    const uint32_t e = tmp / n_rblocks;
-    if (e >= n_envs) return;                                   // warp-uniform
+    uint32_t e = tmp / n_rblocks;
+    // no early exit (keeps the shuffles provably convergent): padding warps redo the last env, stores off
+    const bool warp_ok = e < n_envs;
+    e = warp_ok ? e : n_envs - 1;
 
     Lane L;
     const uint32_t W4 = W >> 2;
     L.rows = rows; L.W = W; L.wrap_rows = wrap_rows;
     L.c4 = cg * 32 + lane;
     L.valid = L.c4 < W4;
+    L.store = L.valid && warp_ok;
     L.edge_l = lane == 0;
     L.edge_r = L.valid && (lane == 31 || L.c4 == W4 - 1);
     L.hidx = L.edge_l ? (L.c4 == 0 ? W - 1 : 4 * L.c4 - 1) : (L.c4 == W4 - 1 ? 0 : 4 * L.c4 + 4);
@@ -102,25 +108,33 @@ life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
     uint32_t *gout = out + (uint64_t)e * rows * W;
 
     const int r0 = (int)(rb * rpt);
-    const int r1 = r0 + (int)rpt;
     RowSums A, B, C;
     row_sums(A, load_row_raw(L, r0 - 1), L);
     row_sums(B, load_row_raw(L, r0), L);
     unsigned pop = 0;
 
-    for (int r = r0; r < r1; r += LIFE_ROWS_PF) {
-        RowRaw raw[LIFE_ROWS_PF];
+    RowRaw nxt[PF];
 #pragma unroll
-        for (int u = 0; u < LIFE_ROWS_PF; ++u) raw[u] = load_row_raw(L, r + u + 1);
+    for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r0 + u + 1);
+
+    for (int i = 0; i < (int)rpt; i += PF) {                   // uniform trip count
+        const int r = r0 + i;
+        RowRaw cur[PF];
 #pragma unroll
-        for (int u = 0; u < LIFE_ROWS_PF; u += 3) {
-            row_sums(C, raw[u], L);     emit_row<COUNT>(A, B, C, gout, L, r + u, pop);
-            row_sums(A, raw[u + 1], L); emit_row<COUNT>(B, C, A, gout, L, r + u + 1, pop);
-            row_sums(B, raw[u + 2], L); emit_row<COUNT>(C, A, B, gout, L, r + u + 2, pop);
+        for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        if (i + PF < (int)rpt) {                               // uniform: prefetch the next trip's rows
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r + PF + u + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < PF; u += 3) {
+            row_sums(C, cur[u], L);     emit_row<COUNT>(A, B, C, gout, L, r + u, pop);
+            row_sums(A, cur[u + 1], L); emit_row<COUNT>(B, C, A, gout, L, r + u + 1, pop);
+            row_sums(B, cur[u + 2], L); emit_row<COUNT>(C, A, B, gout, L, r + u + 2, pop);
         }
     }
     if (COUNT) {
-        if (!L.valid) pop = 0;
+        if (!L.store) pop = 0;
         pop = __reduce_add_sync(0xffffffffu, pop);
         if (lane == 0 && pop) atomicAdd(alive_out + e, pop);
     }
@@ -159,30 +173,22 @@ extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs,
     const uint64_t warps = n_envs * n_cgroups * n_rblocks;
     const uint64_t blocks = (warps + (LIFE_ROWS_THREADS / 32) - 1) / (LIFE_ROWS_THREADS / 32);
     CGL_REQUIRE(blocks < (1ull << 31) && warps < (1ull << 32) && rows < (1u << 30), CGL_E_BADARG, "cgl_life_step: grid too large");
+    static int pf = 0;                           // tuning knob: rows prefetched per thread (3 or 6)
+    if (pf == 0) {
+        const char *v = getenv("CGL_LIFE_PF");
+        pf = (v && atoi(v) == 6) ? 6 : 3;
+    }
     if (alive_out != nullptr) {
         CGL_CUDA(cudaMemsetAsync(alive_out, 0, n_envs * sizeof(uint32_t), st));
-        life_rows_kernel<true><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
+        life_rows_kernel<true, 3><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
             in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, alive_out);
+    } else if (pf == 6) {
+        life_rows_kernel<false, 6><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
+            in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, nullptr);
     } else {
-        life_rows_kernel<false><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
+        life_rows_kernel<false, 3><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
             in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, nullptr);
     }
     CGL_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uint32_t cols,
-                            int wrap_rows, uint32_t gens, uint32_t k, int *result_in_a_out,
-                            cgl_stream_t stream)
-{
-    CGL_REQUIRE(buf_a && buf_b && rows && cols && buf_a != buf_b, CGL_E_BADARG, "cgl_life_run: bad argument");
-    (void)k;   // temporal blocking lands in cgl_life_tb.cu; k = 1 streams
-    uint32_t *src = buf_a, *dst = buf_b;
-    for (uint32_t g = 0; g < gens; ++g) {
-        int rc = cgl_life_step(src, dst, 1, rows, cols, wrap_rows, nullptr, stream);
-        if (rc) return rc;
-        uint32_t *t = src; src = dst; dst = t;
-    }
-    if (result_in_a_out) *result_in_a_out = (src == buf_a) ? 1 : 0;
     return 0;
 }

@@ -33,9 +33,13 @@ def _twin():
 def _cpu_step_factory():
     L = _twin()
 
-    def step(lib, src, dst, rows, cols, wrap_rows, stream):
-        L.twin_life_generic(src.data_ptr(), dst.data_ptr(), 1, rows, cols, wrap_rows)
-    return step
+    def block(lib, a, b, rows, cols, wrap_rows, gens, k, stream):
+        src, dst = a, b
+        for _ in range(gens):
+            L.twin_life_generic(src.data_ptr(), dst.data_ptr(), 1, rows, cols, wrap_rows)
+            src, dst = dst, src
+        return src is a
+    return block
 
 
 def _grid(rows, cols, seed):
@@ -52,7 +56,7 @@ def _worker(rank, world, port, rows, cols, k, gens, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cgl_b200 import bands
-    bands._life_step = _cpu_step_factory()
+    bands._life_block = _cpu_step_factory()
     _, words = _grid(rows, cols, 42)
     b = bands.RowBandLife(rows, cols, k=k, rank=rank, world_size=world, device="cpu", exchange="dist")
     b.set_owned(words[rank * b.band_rows:(rank + 1) * b.band_rows])
@@ -88,8 +92,8 @@ def test_local_bands_emulation_matches_oracle():
     """G bands in one process (local copies instead of peers): the ghost-zone arithmetic alone."""
     sys.path.insert(0, PKG)
     from cgl_b200 import bands
-    old = bands._life_step
-    bands._life_step = _cpu_step_factory()
+    old = bands._life_block
+    bands._life_block = _cpu_step_factory()
     try:
         rows, cols, k, gens = 32, 64, 4, 11
         cells, words = _grid(rows, cols, 7)
@@ -102,4 +106,4 @@ def test_local_bands_emulation_matches_oracle():
         L.twin_unpack(g.data_ptr(), got.ctypes.data, 1, rows, cols)
         assert np.array_equal(got.reshape(rows, cols), oracle.life(cells, gens))
     finally:
-        bands._life_step = old
+        bands._life_block = old

@@ -305,3 +305,41 @@ def test_life_step_vs_oracle(cgl, rows, cols, n_envs, wrap):
         got = _unpack(lib, native, w, n_envs, rows, cols).reshape(n_envs, rows, cols)
         assert np.array_equal(got, cells), (rows, cols, wrap, g)
         assert (alive.cpu().numpy().astype(np.int64) & 0xFFFFFFFF).tolist() == cells.reshape(n_envs, -1).sum(1).tolist()
+
+
+# ------------------------------------------------------------------------------------------
+# temporal blocking: k generations per launch (cgl_life_run)
+# ------------------------------------------------------------------------------------------
+def _life_run(lib, native, a, rows, cols, wrap, gens, k):
+    b = torch.empty_like(a)
+    res = native.ctypes.c_int(-1)
+    native.check(lib.cgl_life_run(native.dptr(a), native.dptr(b), rows, cols, wrap, gens, k,
+                                  native.ctypes.byref(res), native.current_stream()))
+    return a if res.value == 1 else b
+
+
+@pytest.mark.parametrize("rows,cols,gens,k", [(200, 1024, 8, 8), (97, 2048, 13, 4), (64, 960, 5, 2), (300, 4096, 32, 16),
+                                              (128, 1920, 7, 3), (50, 1024, 12, 12), (40, 992, 6, 6), (33, 3104, 9, 1)])
+def test_temporal_blocking_torus_vs_oracle(cgl, rows, cols, gens, k):
+    from cgl_b200 import native
+    lib = native.load()
+    cells = np.random.RandomState(rows * 7 + cols + k).randint(2, size=(rows, cols)).astype(np.uint8)
+    a = _pack(lib, native, cells, 1, rows, cols)
+    out = _life_run(lib, native, a, rows, cols, 1, gens, k)
+    got = _unpack(lib, native, out, 1, rows, cols).reshape(rows, cols)
+    assert np.array_equal(got, oracle.life(cells, gens, threads=4))
+
+
+@pytest.mark.parametrize("rows,cols,k", [(120, 1024, 8), (90, 2048, 4), (200, 960, 16)])
+def test_temporal_blocking_open_band_interior(cgl, rows, cols, k):
+    """wrap_rows=0, one k-block: every row at least k rows from an open edge is exact (ghost-zone contract)."""
+    from cgl_b200 import native
+    lib = native.load()
+    cells = np.random.RandomState(rows + k).randint(2, size=(rows, cols)).astype(np.uint8)
+    a = _pack(lib, native, cells, 1, rows, cols)
+    out = _life_run(lib, native, a, rows, cols, 0, k, k)
+    got = _unpack(lib, native, out, 1, rows, cols).reshape(rows, cols)
+    padded = np.zeros((rows + 2 * k + 2, cols), np.uint8)
+    padded[k + 1:k + 1 + rows] = cells
+    want = oracle.life(padded, k, threads=4)[k + 1:k + 1 + rows]
+    assert np.array_equal(got[k:rows - k], want[k:rows - k])
