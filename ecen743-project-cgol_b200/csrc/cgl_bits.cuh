@@ -89,8 +89,12 @@ CGL_HD uint32_t inc_unless_max4(uint32_t s, uint32_t max4)
 {
     uint32_t x = s ^ max4;                                           // byte == 0  <=>  s == MAX
     uint32_t ne7 = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // bit7 = (byte != 0)
-    uint32_t inc = ne7 >> 7;                                         // 0/1 per byte
-    uint32_t lo = (s & 0x7f7f7f7fu) + inc;                           // carry stops at bit 7
+#if defined(__CUDA_ARCH__)
+    // (ne7 >> 7) + (s & 0x7f..) as ONE multiply-add on the FMA pipe: hi32(ne7 * 2^25) + addend
+    uint32_t lo = __umulhi(ne7, 1u << 25) + (s & 0x7f7f7f7fu);
+#else
+    uint32_t lo = (s & 0x7f7f7f7fu) + (ne7 >> 7);                    // carry stops at bit 7
+#endif
     return lo ^ (s & 0x80808080u);
 }
 

@@ -18,8 +18,9 @@ namespace cgl {
 //
 //   phase 0  the first batch of stability uint4 loads is issued (independent of the bits)
 //   phase A  world words -> shared memory (uint4, coalesced), action bit flipped on the way
-//   phase B  next generation from shared memory (9 LDS + ~12 LOP3 per 32 cells), stored to
-//            HBM; (cur,next) nibbles interleaved into one LUT-index byte per 4 cells
+//   phase B  next generation from shared memory: a thread owns whole rows (vector LDS, in-register
+//            horizontal neighbours, ~22 LOP3/SHF per 32 cells), vector store to HBM; (born,surv)
+//            nibbles interleaved into one table-index byte per 4 cells
 //   phase C  stability stream: LDG.128 -> 4 x {2 conflict-free mask LDS, byte-SIMD update, IDP.4A}
 //            -> STG.128; reward reduced with REDUX + one shared atomic per warp
 // =========================================================================================
@@ -38,6 +39,44 @@ struct EnvCfg {
     static constexpr int SMEM = 4096 + 4096 + EPC * (WPE * 4 + WPE * 8) + EPC * 8;
     static_assert(S % 32 == 0 && NCHUNK % TPE == 0 && WPE % 4 == 0, "unsupported side");
 };
+
+// N consecutive words (N*4-byte aligned base) with the widest vector accesses available.
+template <int N>
+__device__ __forceinline__ void load_words(const uint32_t *p, uint32_t (&x)[N])
+{
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const uint2 v = reinterpret_cast<const uint2 *>(p)[i];
+            x[2 * i] = v.x; x[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = p[i];
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_words(uint32_t *p, const uint32_t (&x)[N])
+{
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i)
+            reinterpret_cast<uint4 *>(p)[i] = make_uint4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) reinterpret_cast<uint2 *>(p)[i] = make_uint2(x[2 * i], x[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = x[i];
+    }
+}
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 {
@@ -114,26 +153,39 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     __syncthreads();
 
     // ---- phase B: next generation ------------------------------------------------------------
+    // A thread owns RPB consecutive rows at full width (W words): vector LDS of whole rows,
+    // horizontal neighbours (incl. the torus wrap) stay in registers, one vector store per row.
     uint32_t pop = 0;
     if (active) {
         uint32_t *wo = world_out + (size_t)e * C::WPE;
+        constexpr int RPB = S / C::TPE;            // rows per thread (1 or 2)
+        HSum hs[RPB + 2][C::W];
+        uint32_t cw[RPB + 2][C::W];
 #pragma unroll
-        for (int j = 0; j < C::WPE / C::TPE; ++j) {
-            const int i = t + j * C::TPE;
-            const int r = i / C::W, w = i % C::W;
-            const int ru = (r == 0 ? S - 1 : r - 1) * C::W, rc = r * C::W,
-                      rd = (r == S - 1 ? 0 : r + 1) * C::W;
-            const int wl = (w == 0 ? C::W - 1 : w - 1), wr = (w == C::W - 1 ? 0 : w + 1);
-            const uint32_t a = cur[ru + w], c = cur[rc + w], b = cur[rd + w];
-            const HSum ha = hsum(west_plane(cur[ru + wl], a), a, east_plane(a, cur[ru + wr]));
-            const HSum hc = hsum(west_plane(cur[rc + wl], c), c, east_plane(c, cur[rc + wr]));
-            const HSum hb = hsum(west_plane(cur[rd + wl], b), b, east_plane(b, cur[rd + wr]));
-            const uint32_t nxt = life_rule(ha, hc, hb, c);
-            wo[i] = nxt;
-            pop += __popc(nxt);
-            uint32_t lo, hi;                      // byte per 4 cells: born nibble << 4 | surv nibble
-            mix_nibbles(nxt & ~c, nxt & c, lo, hi);
-            reinterpret_cast<uint2 *>(mix)[i] = make_uint2(lo, hi);
+        for (int j = 0; j < RPB + 2; ++j) {
+            int r = t * RPB + j - 1;
+            r = r < 0 ? S - 1 : (r >= S ? 0 : r);
+            load_words<C::W>(cur + r * C::W, cw[j]);
+#pragma unroll
+            for (int w = 0; w < C::W; ++w)
+                hs[j][w] = hsum(west_plane(cw[j][(w + C::W - 1) % C::W], cw[j][w]), cw[j][w],
+                                east_plane(cw[j][w], cw[j][(w + 1) % C::W]));
+        }
+#pragma unroll
+        for (int j = 0; j < RPB; ++j) {
+            const int r = t * RPB + j;
+            uint32_t nx[C::W], mx[2 * C::W];
+#pragma unroll
+            for (int w = 0; w < C::W; ++w) {
+                const uint32_t c = cw[j + 1][w];
+                const uint32_t nxt = life_rule(hs[j][w], hs[j + 1][w], hs[j + 2][w], c);
+                nx[w] = nxt;
+                pop += __popc(nxt);
+                // byte per 4 cells: born nibble << 4 | surv nibble
+                mix_nibbles(nxt & ~c, nxt & c, mx[2 * w], mx[2 * w + 1]);
+            }
+            store_words<C::W>(wo + r * C::W, nx);
+            store_words<2 * C::W>(mix + 2 * r * C::W, mx);
         }
     }
     __syncthreads();

@@ -49,9 +49,18 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
 
     const int r0 = (int)(rb * rpt);
     const int r1 = (r0 + (int)rpt < (int)rows) ? r0 + (int)rpt : (int)rows;
-    const int rstart = r0 - K;
-    const int n_steps = (int)rpt + 3 * K - 1;                   // same trip count for every warp (uniform loop)
     const int irows = (int)rows;
+    const int rstart = r0 - K;                                  // first gen-0 row fed to level 1 (> -rows)
+    const int n_steps = (int)rpt + 3 * K - 1;                   // same trip count for every warp (uniform loop)
+    // Step s loads gen-0 row rstart + s.  It is needed (and inside the grid, for open rows) iff
+    // s_lo <= s < s_hi; rows from r1 + K on can no longer reach an output row of this strip.
+    const int s_lo = wrap_rows ? 0 : (rstart < 0 ? -rstart : 0);
+    const int last = (wrap_rows || r1 + K < irows) ? r1 + K : irows;
+    const uint32_t span = (uint32_t)(last - rstart - s_lo);
+    const uint32_t out_rows = (uint32_t)(r1 - r0);
+    int rw = rstart < 0 ? rstart + irows : rstart;              // row index modulo rows (only used where loads are on)
+    const uint32_t *ip = in + wcol;
+    uint32_t *op = out + (store_ok ? (uint32_t)wi : 0u);
 
     Win win[K];
     uint32_t pend[K];                   // pend[g] = output of level g+1 at the previous step
@@ -65,13 +74,12 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
         uint32_t raw[TB_UNROLL];
 #pragma unroll
         for (int u = 0; u < TB_UNROLL; ++u) {
-            const int r = rstart + s0 + u;
-            const bool outside = (r < 0) | (r >= irows);
-            const int rw = r < 0 ? r + irows : (r >= irows ? r - irows : r);
+            const uint32_t ru = umin((uint32_t)rw + u, (uint32_t)rw + u - rows);      // (rw + u) mod rows
             raw[u] = 0;
-            // rows below r1 + K - 1 can no longer reach an output row of this strip
-            if ((!outside | (wrap_rows != 0)) && r < r1 + K) raw[u] = __ldg(in + (uint64_t)(uint32_t)rw * W + wcol);
+            if ((uint32_t)(s0 + u - s_lo) < span) raw[u] = __ldg(ip + ru * W);          // rows * W < 2^32
         }
+        rw += TB_UNROLL;
+        rw = rw >= irows ? rw - irows : rw;
 #pragma unroll
         for (int u = 0; u < TB_UNROLL; ++u) {
             // levels in descending order: level g+1 reads pend[g-1] before level g overwrites it
@@ -87,8 +95,9 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
                 win[g].us0 = win[g].ms0; win[g].us1 = win[g].ms1;
                 win[g].ms0 = d.s0; win[g].ms1 = d.s1; win[g].mt0 = d.t0; win[g].mt1 = d.t1; win[g].mc = x;
             }
-            const int ro = r0 + s0 + u - (3 * K - 1);          // row of generation K that just left level K
-            if (store_ok && ro >= r0 && ro < r1) out[(uint64_t)(uint32_t)ro * W + (uint32_t)wi] = pend[K - 1];
+            // row r0 + so of generation K has just left level K
+            const uint32_t so = (uint32_t)(s0 + u - (3 * K - 1));
+            if (store_ok && so < out_rows) op[((uint32_t)r0 + so) * W] = pend[K - 1];
         }
     }
 }
@@ -113,7 +122,8 @@ static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t 
     const uint32_t n_rblocks = (rows + rpt - 1) / rpt;
     const uint64_t warps = (uint64_t)n_cgroups * n_rblocks;
     const uint64_t blocks = (warps + (TB_THREADS / 32) - 1) / (TB_THREADS / 32);
-    CGL_REQUIRE(blocks < (1ull << 31) && rows < (1u << 30), CGL_E_BADARG, "cgl_life_run: grid too large");
+    CGL_REQUIRE(blocks < (1ull << 31) && rows < (1u << 30) && (uint64_t)rows * W < (1ull << 32), CGL_E_BADARG,
+                "cgl_life_run: grid too large for the k-blocked kernel (rows * cols/32 must be < 2^32)");
     life_tb_kernel<K><<<(unsigned)blocks, TB_THREADS, 0, st>>>(in, out, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks);
     CGL_LAUNCH_CHECK();
     return 0;
