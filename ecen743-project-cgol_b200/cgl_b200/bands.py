@@ -12,7 +12,12 @@ in from the buffer edges advances one row per generation and never reaches an ow
 Horizontal wrap is local.  Message = k * C/8 bytes per neighbour per k generations.
 
 Exchange back ends
-  "p2p"   (default on GPUs) CUDA-IPC peer stores over NVLink: `cgl_halo_push` writes the strip
+  "fused" the halo exchange lives INSIDE the k-generation kernel
+          (`cgl_life_band_block`): the strips that produce a rank's first/last k owned rows store
+          them straight into the neighbours' next input buffers over NVLink (CUDA-IPC mapped peer
+          memory) and bump an arrival counter; only the strips that read ghost rows wait for the
+          neighbours' previous block.  No exchange launches, no host sync, interior strips never wait.
+  "p2p"   (default on GPUs) one exchange launch per block (`cgl_halo_exchange`, 2 CTAs): writes the strip
           straight into the neighbour's landing zone and publishes a sequence flag;
           `cgl_halo_wait_copy` on the neighbour spins on the flag and moves the strip into its
           ghost rows.  Two landing slots alternate by block parity, so a rank may run one block
@@ -68,12 +73,17 @@ class RowBandLife:
         self.ghost = g
         self.buf_rows = self.band_rows + 2 * g
         n = self.buf_rows * self.W
-        self._a = torch.zeros(n, dtype=torch.int32, device=self.device)
-        self._b = torch.zeros(n, dtype=torch.int32, device=self.device)
         self.generation = 0
         self.block = 0              # exchanges done so far
         self.launches = 0
         self._ipc = None
+        self._fused = None
+        self._ghosts_valid = False
+        if self.exchange == "fused" and self.G > 1:
+            self._setup_fused(n)    # band buffers must be whole cudaMalloc allocations (IPC)
+        else:
+            self._a = torch.zeros(n, dtype=torch.int32, device=self.device)
+            self._b = torch.zeros(n, dtype=torch.int32, device=self.device)
         if self.exchange == "p2p" and self.G > 1:
             self._setup_p2p()
 
@@ -91,6 +101,7 @@ class RowBandLife:
 
     def set_owned(self, words: torch.Tensor) -> None:
         self.owned.copy_(words.view(self.band_rows, self.W))
+        self._ghosts_valid = False
 
     def randomize(self, seed: int = 0) -> None:
         """Synthetic Bernoulli(0.5) start: every packed word uniform, seeded by GLOBAL row so that the
@@ -102,6 +113,43 @@ class RowBandLife:
             g.manual_seed(seed * 1000003 + (r0 + s))
             self.owned[s:s + chunk] = torch.randint(-2 ** 31, 2 ** 31 - 1, (chunk, self.W), dtype=torch.int32,
                                                     device=self.device, generator=g)
+        self._ghosts_valid = False
+
+    # ---------------------------------------------------------------- fused-exchange plumbing
+    def _alloc_shared(self, nbytes):
+        """cudaMalloc'ed (IPC-exportable) memory + its handle."""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            native.check(self.lib.cgl_dev_alloc(nbytes, ctypes.byref(ptr)), "cgl_dev_alloc")
+            native.check(self.lib.cgl_ipc_get_handle(ptr, handle), "cgl_ipc_get_handle")
+        return ptr.value, bytes(handle)
+
+    def _as_tensor(self, ptr, n_words):
+        class _Raw:     # zero-copy int32 view of raw device memory
+            __cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def _setup_fused(self, n_words):
+        import torch.distributed as dist
+        mine = [self._alloc_shared(n_words * 4), self._alloc_shared(n_words * 4), self._alloc_shared(256)]
+        self._a = self._as_tensor(mine[0][0], n_words)
+        self._b = self._as_tensor(mine[1][0], n_words)
+        handles = [None] * self.G
+        dist.all_gather_object(handles, [h for _, h in mine], group=self.group)
+        up, down = (self.rank - 1) % self.G, (self.rank + 1) % self.G
+        peers = {}
+        with torch.cuda.device(self.device):
+            for p in {up, down}:
+                ptrs = []
+                for h in handles[p]:
+                    ptr = ctypes.c_void_p()
+                    native.check(self.lib.cgl_ipc_open_handle((ctypes.c_uint8 * 64).from_buffer_copy(h), ctypes.byref(ptr)),
+                                 "cgl_ipc_open_handle")
+                    ptrs.append(ptr.value)
+                peers[p] = ptrs
+        self._fused = dict(mine=[m[0] for m in mine], up=peers[up], down=peers[down], peers=peers, block_index=0)
+        dist.barrier(group=self.group)
 
     # ---------------------------------------------------------------- P2P plumbing
     def _setup_p2p(self):
@@ -130,6 +178,20 @@ class RowBandLife:
         dist.barrier(group=self.group)
 
     def close(self):
+        if self._fused:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            f = self._fused
+            self._a = self._b = None
+            with torch.cuda.device(self.device):
+                for ptrs in f["peers"].values():
+                    for p in ptrs:
+                        self.lib.cgl_ipc_close_handle(ctypes.c_void_p(p))
+                dist.barrier(group=self.group)
+                for p in f["mine"]:
+                    self.lib.cgl_dev_free(ctypes.c_void_p(p))
+            self._fused = None
         if self._ipc:
             import torch.distributed as dist
             torch.cuda.synchronize(self.device)
@@ -152,7 +214,7 @@ class RowBandLife:
         ghost_up = a[0:k * W]
         ghost_down = a[(g + self.band_rows) * W:(g + self.band_rows + k) * W]
         self.block += 1
-        if self.exchange == "dist":
+        if self.exchange in ("dist", "fused"):      # fused: only to (re)fill the ghosts of a fresh grid
             import torch.distributed as dist
             up, down = (self.rank - 1) % self.G, (self.rank + 1) % self.G
             send_up, send_down = top_owned.clone(), bot_owned.clone()
@@ -168,21 +230,17 @@ class RowBandLife:
             strip, slot, seq = ipc["strip"], self.block & 1, self.block
             n_words = k * W
             # my top rows are the neighbour-above's "from_down" strip; my bottom rows the neighbour-below's "from_up"
+            base, fo = ipc["base"], ipc["flags_off"]
+            V = ctypes.c_void_p
             with torch.cuda.device(self.device):
-                native.check(lib.cgl_halo_push(native.dptr(top_owned), ctypes.c_void_p(ipc["up"] + (2 * slot + 1) * strip),
-                                               n_words, ctypes.c_void_p(ipc["up"] + ipc["flags_off"] + 4 * (2 * slot + 1)),
-                                               seq, st), "cgl_halo_push")
-                native.check(lib.cgl_halo_push(native.dptr(bot_owned), ctypes.c_void_p(ipc["down"] + (2 * slot) * strip),
-                                               n_words, ctypes.c_void_p(ipc["down"] + ipc["flags_off"] + 4 * (2 * slot)),
-                                               seq, st), "cgl_halo_push")
-                base = ipc["base"]
-                native.check(lib.cgl_halo_wait_copy(ctypes.c_void_p(base + ipc["flags_off"] + 4 * (2 * slot)), seq,
-                                                    ctypes.c_void_p(base + (2 * slot) * strip), native.dptr(ghost_up),
-                                                    n_words, st), "cgl_halo_wait_copy")
-                native.check(lib.cgl_halo_wait_copy(ctypes.c_void_p(base + ipc["flags_off"] + 4 * (2 * slot + 1)), seq,
-                                                    ctypes.c_void_p(base + (2 * slot + 1) * strip), native.dptr(ghost_down),
-                                                    n_words, st), "cgl_halo_wait_copy")
-            self.launches += 4
+                native.check(lib.cgl_halo_exchange(
+                    native.dptr(top_owned), native.dptr(bot_owned),
+                    V(ipc["up"] + (2 * slot + 1) * strip), V(ipc["down"] + (2 * slot) * strip),
+                    V(ipc["up"] + fo + 4 * (2 * slot + 1)), V(ipc["down"] + fo + 4 * (2 * slot)),
+                    V(base + (2 * slot) * strip), V(base + (2 * slot + 1) * strip),
+                    V(base + fo + 4 * (2 * slot)), V(base + fo + 4 * (2 * slot + 1)),
+                    native.dptr(ghost_up), native.dptr(ghost_down), n_words, seq, st), "cgl_halo_exchange")
+            self.launches += 1
             return
         raise ValueError(f"unknown exchange {self.exchange!r}")
 
@@ -190,6 +248,13 @@ class RowBandLife:
     def run(self, gens: int) -> None:
         """Advance `gens` generations (blocks of k generations between exchanges)."""
         lib, st = self.lib, self._stream()
+        if self.device.type == "cuda" and self.exchange != "fused" and not getattr(self, "_tuned", False):
+            # measure the strip length of the k-blocked kernel for this band shape once (clobbers _b only)
+            with torch.cuda.device(self.device):
+                native.check(lib.cgl_life_tune(native.dptr(self._a), native.dptr(self._b),
+                                               self.band_rows if self.G == 1 else self.buf_rows, self.cols,
+                                               1 if self.G == 1 else 0, self.k, st), "cgl_life_tune")
+            self._tuned = True
         if self.G == 1:                      # plain torus: one call, k generations per launch
             with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
                 if not _life_block(lib, self._a, self._b, self.band_rows, self.cols, 1, gens, self.k, st):
@@ -197,6 +262,8 @@ class RowBandLife:
             self.launches += -(-gens // self.k)
             self.generation += gens
             return
+        if self.exchange == "fused":
+            return self._run_fused(gens)
         done = 0
         while done < gens:
             kb = min(self.k, gens - done)
@@ -204,6 +271,40 @@ class RowBandLife:
             with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
                 if not _life_block(lib, self._a, self._b, self.buf_rows, self.cols, 0, kb, kb, st):
                     self._a, self._b = self._b, self._a
+            self.launches += 1
+            done += kb
+            self.generation += kb
+
+    _BLOCK_SIZES = (16, 12, 8, 6, 4, 3, 2, 1)       # generations one fused launch can do
+
+    def _run_fused(self, gens: int) -> None:
+        import torch.distributed as dist
+        f, lib, st = self._fused, self.lib, self._stream()
+        if not self._ghosts_valid:
+            # fresh grid: fill the ghost rows once with a plain exchange and restart the counters
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self._exchange()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                native.check(lib.cgl_dev_memset(ctypes.c_void_p(f["mine"][2]), 0, 256, st), "cgl_dev_memset")
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            f["block_index"] = 0
+            self._ghosts_valid = True
+        done = 0
+        while done < gens:
+            kb = next(s for s in self._BLOCK_SIZES if s <= min(self.k, gens - done))
+            f["block_index"] += 1
+            cur_is_a = self._a.data_ptr() == f["mine"][0]
+            i_in, i_out = (0, 1) if cur_is_a else (1, 0)
+            with torch.cuda.device(self.device):
+                native.check(lib.cgl_life_band_block(
+                    ctypes.c_void_p(f["mine"][i_in]), ctypes.c_void_p(f["mine"][i_out]), self.buf_rows, self.cols,
+                    self.ghost, kb, ctypes.c_void_p(f["up"][i_out]), ctypes.c_void_p(f["down"][i_out]),
+                    ctypes.c_void_p(f["up"][2]), ctypes.c_void_p(f["down"][2]), ctypes.c_void_p(f["mine"][2]),
+                    f["block_index"], st), "cgl_life_band_block")
+            self._a, self._b = self._b, self._a
             self.launches += 1
             done += kb
             self.generation += kb

@@ -40,6 +40,7 @@ SIGNATURES = {
     "cgl_env_step_launches": (_i, [_u32, _i]),
     "cgl_life_step": (_i, [_vp, _vp, _u64, _u32, _u32, _i, _vp, _vp]),
     "cgl_life_run": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _u32, ctypes.POINTER(_i), _vp]),
+    "cgl_life_tune": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _vp]),
     "cgl_reward": (_i, [_vp, _u64, _u64, _vp, _vp]),
     "cgl_alive": (_i, [_vp, _u64, _u64, _vp, _vp]),
     "cgl_match": (_i, [_vp, _vp, _u64, _vp, _vp]),
@@ -49,10 +50,13 @@ SIGNATURES = {
     "cgl_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),
     "cgl_ipc_close_handle": (_i, [_vp]),
     "cgl_halo_push": (_i, [_vp, _vp, _u64, _vp, _u32, _vp]),
+    "cgl_halo_exchange": (_i, [_vp] * 12 + [_u64, _u32, _vp]),
     "cgl_halo_wait": (_i, [_vp, _u32, _vp]),
     "cgl_halo_wait_copy": (_i, [_vp, _u32, _vp, _vp, _u64, _vp]),
+    "cgl_life_band_block": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "cgl_dev_alloc": (_i, [_u64, ctypes.POINTER(_vp)]),
     "cgl_dev_free": (_i, [_vp]),
+    "cgl_dev_memset": (_i, [_vp, _i, _u64, _vp]),
 }
 
 _lib = None

@@ -63,9 +63,55 @@ __global__ void halo_wait_copy_kernel(const uint32_t *flag, uint32_t seq, const 
     for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
 }
 
+// Whole halo exchange of one rank in ONE launch: CTA 0 talks to the upper neighbour, CTA 1 to the
+// lower one.  Each pushes its strip into the neighbour's landing slot and publishes `seq`, then waits
+// for the neighbour's strip of the same block and moves it into its own ghost rows.  Every rank
+// pushes before it waits, so the ring cannot deadlock.
+struct HaloSide {
+    const uint4 *src;        // my boundary rows
+    uint4 *peer_landing;     // neighbour's landing slot for them
+    uint32_t *peer_flag;
+    const uint32_t *my_flag; // set by that neighbour
+    const uint4 *my_landing;
+    uint4 *ghost;            // my ghost rows on that side
+};
+
+__global__ void __launch_bounds__(1024) halo_exchange_kernel(HaloSide up, HaloSide dn, uint64_t n_vec, uint32_t seq)
+{
+    const HaloSide s = blockIdx.x == 0 ? up : dn;
+    for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) s.peer_landing[i] = s.src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.peer_flag), "r"(seq) : "memory");
+        spin_until(s.my_flag, seq);
+    }
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) s.ghost[i] = __ldcg(s.my_landing + i);
+}
+
 }  // namespace cgl
 
 using namespace cgl;
+
+extern "C" int cgl_halo_exchange(const uint32_t *top_src, const uint32_t *bot_src, uint32_t *peer_up_landing,
+                                 uint32_t *peer_dn_landing, uint32_t *peer_up_flag, uint32_t *peer_dn_flag,
+                                 const uint32_t *my_landing_up, const uint32_t *my_landing_dn,
+                                 const uint32_t *my_flag_up, const uint32_t *my_flag_dn, uint32_t *ghost_up,
+                                 uint32_t *ghost_dn, uint64_t n_words, uint32_t seq, cgl_stream_t stream)
+{
+    CGL_REQUIRE(top_src && bot_src && peer_up_landing && peer_dn_landing && peer_up_flag && peer_dn_flag &&
+                my_landing_up && my_landing_dn && my_flag_up && my_flag_dn && ghost_up && ghost_dn && n_words &&
+                n_words % 4 == 0, CGL_E_BADARG, "cgl_halo_exchange: bad argument");
+    HaloSide up{reinterpret_cast<const uint4 *>(top_src), reinterpret_cast<uint4 *>(peer_up_landing), peer_up_flag,
+                my_flag_up, reinterpret_cast<const uint4 *>(my_landing_up), reinterpret_cast<uint4 *>(ghost_up)};
+    HaloSide dn{reinterpret_cast<const uint4 *>(bot_src), reinterpret_cast<uint4 *>(peer_dn_landing), peer_dn_flag,
+                my_flag_dn, reinterpret_cast<const uint4 *>(my_landing_dn), reinterpret_cast<uint4 *>(ghost_dn)};
+    halo_exchange_kernel<<<2, 1024, 0, as_stream(stream)>>>(up, dn, n_words / 4, seq);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int cgl_abi_version(void) { return CGL_B200_ABI_VERSION; }
 extern "C" const char *cgl_last_error(void) { return g_err; }
@@ -221,6 +267,13 @@ extern "C" int cgl_dev_alloc(uint64_t bytes, void **dev_ptr_out)
     CGL_REQUIRE(bytes && dev_ptr_out, CGL_E_BADARG, "cgl_dev_alloc: bad argument");
     CGL_CUDA(cudaMalloc(dev_ptr_out, bytes));
     CGL_CUDA(cudaMemset(*dev_ptr_out, 0, bytes));
+    return 0;
+}
+
+extern "C" int cgl_dev_memset(void *dev_ptr, int value, uint64_t bytes, cgl_stream_t stream)
+{
+    CGL_REQUIRE(dev_ptr && bytes, CGL_E_BADARG, "cgl_dev_memset: bad argument");
+    CGL_CUDA(cudaMemsetAsync(dev_ptr, value, bytes, as_stream(stream)));
     return 0;
 }
 

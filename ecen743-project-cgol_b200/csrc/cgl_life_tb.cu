@@ -25,21 +25,70 @@ struct Win {            // window of one level: rows (a-1, a) of the level's inp
     uint32_t ms0, ms1, mt0, mt1, mc;    // row a: sums with / without the centre, and the centre word
 };
 
-constexpr int TB_THREADS = 128;
+// Tried and measured on B200 (profiles/r01_sweeps.md): moving the two funnel shifts to the FMA pipe
+// (IMAD / IMAD.HI with opaque multipliers) is 6 % SLOWER although the kernel is ALU-pipe bound, and
+// one-warp CTAs are 12 % slower than 4-warp CTAs, and mapping a whole CTA to one row block (loop
+// bounds in uniform registers) is 7 % slower than the warp-linear mapping below; all removed again.
+// Fused halo exchange (row bands over NVLink, one process per GPU).  With HALO the kernel
+//   * stores locally only the rows this rank owns ([store_lo, store_hi) of its band buffer),
+//   * stores the first / last `depth` owned rows ALSO straight into the ghost rows of the ring
+//     neighbours' output buffers (peer-mapped pointers: plain st.global over NVLink),
+//   * a strip that pushed bumps the neighbour's arrival counter (system-scope release) when it is
+//     done, and a strip that reads ghost rows first waits until its own counters show that BOTH
+//     neighbours finished the previous block (acquire) -- interior strips never wait, so the
+//     exchange overlaps the compute and costs no extra launch.
+struct HaloCtx {
+    uint32_t store_lo, store_hi;          // owned rows of the band buffer
+    uint32_t depth;                       // ghost depth = rows pushed per direction
+    uint32_t *push_up, *push_dn;          // peer: where my row store_lo / my row store_hi - depth lands
+    uint32_t *sig_up, *sig_dn;            // peer arrival counters
+    const uint32_t *wait_up, *wait_dn;    // my arrival counters (filled by the neighbours)
+    uint32_t wait_up_target, wait_dn_target;
+};
+
+// Spin until *ctr - target >= 0 (acquire, system scope); lane 0 polls, the warp follows.
+__device__ __forceinline__ void wait_counter(const uint32_t *ctr, uint32_t target)
+{
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (__any_sync(0xffffffffu, (int32_t)(v - target) < 0));      // warp-uniform exit
+}
+
+// Predicated store: `if (ok && a < b) *p = v` as ONE predicated STG.  Written in PTX on purpose: the
+// row-range test is CTA-uniform, and for a uniform condition the compiler emits a branch around the
+// store, which splits the 6-step unrolled body into basic blocks and costs ~8 % (measured) because
+// independent levels of neighbouring steps can no longer be interleaved.
+__device__ __forceinline__ void st_if_lt(uint32_t *p, uint32_t v, bool ok, uint32_t a, uint32_t b)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.u32 p, %2, %3;\n\t"
+        "setp.ne.u32 q, %4, 0;\n\t"
+        "and.pred p, p, q;\n\t"
+        "@p st.global.u32 [%0], %1;\n\t}"
+        ::"l"(p), "r"(v), "r"(a), "r"(b), "r"((uint32_t)ok) : "memory");
+}
+
 constexpr int TB_UNROLL = 6;            // row steps per loop trip (loads issued up front)
 constexpr int TB_COLS = 30;             // valid word-columns per warp
 
-template <int K>
+constexpr int TB_THREADS = 128;
+
+// (Capping the fused-exchange variant at the plain kernel's 96 registers spills and is slower.)
+template <int K, bool HALO>
 __global__ void __launch_bounds__(TB_THREADS)
 life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t rows, uint32_t W,
-               uint32_t rpt, int wrap_rows, uint32_t n_cgroups, uint32_t n_rblocks)
+               uint32_t rpt, int wrap_rows, uint32_t n_cgroups, uint32_t n_rblocks, const HaloCtx hc)
 {
+    // Warps are numbered along the row first (column group fastest).  No early exit: padding warps
+    // redo the last strip with stores off, the loop trip count is the same for every warp, and the
+    // halo waits are branch-free PTX -- so every shuffle below is provably convergent (plain SHFL;
+    // a divergence fallback path costs ~8 %).
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5);
     const uint32_t cg = warp % n_cgroups;
     uint32_t rb = warp / n_cgroups;
-    // no early exit: padding warps redo the last strip with stores off, so that every shuffle
-    // below is provably convergent (plain SHFL, no divergence fallback path)
     const bool warp_ok = rb < n_rblocks;
     rb = warp_ok ? rb : n_rblocks - 1;
 
@@ -62,6 +111,18 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
     const uint32_t *ip = in + wcol;
     uint32_t *op = out + (store_ok ? (uint32_t)wi : 0u);
 
+    // HALO: does this strip push rows to a neighbour / read ghost rows?  (warp-uniform)
+    bool push_up = false, push_dn = false;
+    if (HALO) {
+        push_up = warp_ok && (uint32_t)r0 < hc.store_lo + hc.depth && (uint32_t)r1 > hc.store_lo;
+        push_dn = warp_ok && (uint32_t)r0 < hc.store_hi && (uint32_t)r1 + hc.depth > hc.store_hi;
+        const bool reads_up = r0 - K < (int)hc.store_lo, reads_dn = (uint32_t)(r1 + K) > hc.store_hi;
+        // unconditional (branch-free): strips that need nothing wait for target 0, i.e. not at all
+        wait_counter(hc.wait_up, (reads_up || push_up) ? hc.wait_up_target : 0u);
+        wait_counter(hc.wait_dn, (reads_dn || push_dn) ? hc.wait_dn_target : 0u);
+    }
+
+    const uint32_t owned_rows = HALO ? hc.store_hi - hc.store_lo : 0u;
     Win win[K];
     uint32_t pend[K];                   // pend[g] = output of level g+1 at the previous step
 #pragma unroll
@@ -76,7 +137,8 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
         for (int u = 0; u < TB_UNROLL; ++u) {
             const uint32_t ru = umin((uint32_t)rw + u, (uint32_t)rw + u - rows);      // (rw + u) mod rows
             raw[u] = 0;
-            if ((uint32_t)(s0 + u - s_lo) < span) raw[u] = __ldg(ip + ru * W);          // rows * W < 2^32
+            if ((uint32_t)(s0 + u - s_lo) < span)                                       // rows * W < 2^32
+                raw[u] = HALO ? __ldcg(ip + ru * W) : __ldg(ip + ru * W);               // ghost rows: L2 only
         }
         rw += TB_UNROLL;
         rw = rw >= irows ? rw - irows : rw;
@@ -97,51 +159,119 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
             }
             // row r0 + so of generation K has just left level K
             const uint32_t so = (uint32_t)(s0 + u - (3 * K - 1));
-            if (store_ok && so < out_rows) op[((uint32_t)r0 + so) * W] = pend[K - 1];
+            const uint32_t ro = (uint32_t)r0 + so;
+            if (!HALO) {
+                st_if_lt(op + ro * W, pend[K - 1], store_ok, so, out_rows);
+            } else {
+                const bool in_strip = store_ok && so < out_rows;
+                const uint32_t rel = ro - hc.store_lo;             // row within the owned range
+                st_if_lt(op + ro * W, pend[K - 1], in_strip, rel, owned_rows);
+                st_if_lt(hc.push_up + rel * W + (uint32_t)wi, pend[K - 1], in_strip, rel, hc.depth);
+                st_if_lt(hc.push_dn + (rel - (owned_rows - hc.depth)) * W + (uint32_t)wi, pend[K - 1],
+                         in_strip && rel < owned_rows, owned_rows - 1 - rel, hc.depth);
+            }
+        }
+    }
+    if (HALO) {
+        __threadfence_system();                      // my peer stores are visible system-wide ...
+        __syncwarp();
+        if (lane == 0 && warp_ok) {                  // ... before the arrival is published
+            __threadfence_system();
+            if (push_up) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(hc.sig_up) : "memory");
+            if (push_dn) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(hc.sig_dn) : "memory");
         }
     }
 }
 
-template <int K>
-static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t cols, int wrap_rows,
-                     cudaStream_t st)
+// Strip length for a (rows x cols) grid.  A strip costs rpt + 3K - 1 row steps (pipeline fill), and
+// the grid runs in ceil(CTAs / resident CTAs) waves of equally long CTAs; pick the candidate that
+// minimises waves x steps (measured on B200, profiles/r01_sweeps.md: both effects are real, and
+// fewer than ~3 waves balance badly, which the 0.97 factor for >= 3 waves encodes).
+static uint32_t tb_pick_rows(uint32_t rows, uint32_t n_cgroups, int K, uint64_t slot_ctas)
 {
-    static int rpt_knob = -1;
+    static const uint32_t cand[] = {96, 128, 160, 192, 224, 256, 320, 384, 448, 512, 640, 768, 1024};
+    uint32_t best = 256;
+    double best_t = 1e30;
+    for (uint32_t rpt : cand) {
+        if (rpt < 8u * K) continue;
+        const uint32_t eff = rpt < rows ? rpt : rows;
+        const uint64_t warps = (uint64_t)n_cgroups * ((rows + eff - 1) / eff);
+        const uint64_t ctas = (warps + TB_THREADS / 32 - 1) / (TB_THREADS / 32);
+        const uint64_t waves = (ctas + slot_ctas - 1) / slot_ctas;
+        double t = (double)waves * (eff + 3 * K - 1);
+        if (waves >= 3) t *= 0.97;
+        if (t < best_t) { best_t = t; best = eff; }
+    }
+    return best;
+}
+
+// Strip lengths measured by cgl_life_tune for a (rows, words per row, K) shape.
+struct TunedRows { uint32_t rows, W; int K; uint32_t rpt; };
+static TunedRows g_tuned[64];
+static int g_n_tuned = 0;
+
+static uint32_t tuned_rows(uint32_t rows, uint32_t W, int K)
+{
+    for (int i = 0; i < g_n_tuned; ++i)
+        if (g_tuned[i].rows == rows && g_tuned[i].W == W && g_tuned[i].K == K) return g_tuned[i].rpt;
+    return 0;
+}
+
+// Strips (per column group) whose output rows intersect [lo, hi).
+static uint32_t strips_touching(uint32_t lo, uint32_t hi, uint32_t rpt, uint32_t rows)
+{
+    if (hi > rows) hi = rows;
+    if (lo >= hi) return 0;
+    return (hi - 1) / rpt - lo / rpt + 1;
+}
+
+// HALO launches: `halo` carries the pointers; *_target are filled in here from `block_index`
+// (1-based count of band blocks since the ghosts were last filled by a plain exchange).
+template <int K, bool HALO>
+static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t cols, int wrap_rows,
+                     cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0)
+{
+    static int rpt_knob = -1, occ = 0;   // CGL_TB_ROWS overrides the strip length (tuning)
     if (rpt_knob < 0) {
         const char *e = getenv("CGL_TB_ROWS");
         rpt_knob = e ? atoi(e) : 0;
+        int n = 0;
+        CGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, life_tb_kernel<K, HALO>, TB_THREADS, 0));
+        occ = n > 0 ? n : 1;
     }
     const uint32_t W = cols / 32;
     const uint32_t n_cgroups = (W + TB_COLS - 1) / TB_COLS;
-    // strip length: long enough to amortise the 3K-1 fill steps, short enough for >= ~4 waves of warps
-    uint32_t rpt = rpt_knob > 0 ? (uint32_t)rpt_knob : 64u * K;
-    if (rpt < 64) rpt = 64;
-    const uint64_t want = (uint64_t)sm_count() * 16 * 4;
-    while (rpt > 24u * K && rpt > 32 && (uint64_t)n_cgroups * ((rows + rpt - 1) / rpt) < want && rpt_knob <= 0) rpt >>= 1;
+    uint32_t rpt = rpt_knob > 0 ? (uint32_t)rpt_knob : (HALO ? 0u : tuned_rows(rows, W, K));
+    if (rpt == 0) rpt = tb_pick_rows(rows, n_cgroups, K, (uint64_t)sm_count() * occ);
     if (rpt > rows) rpt = rows;
     const uint32_t n_rblocks = (rows + rpt - 1) / rpt;
-    const uint64_t warps = (uint64_t)n_cgroups * n_rblocks;
-    const uint64_t blocks = (warps + (TB_THREADS / 32) - 1) / (TB_THREADS / 32);
+    const uint64_t blocks = ((uint64_t)n_cgroups * n_rblocks + TB_THREADS / 32 - 1) / (TB_THREADS / 32);
     CGL_REQUIRE(blocks < (1ull << 31) && rows < (1u << 30) && (uint64_t)rows * W < (1ull << 32), CGL_E_BADARG,
                 "cgl_life_run: grid too large for the k-blocked kernel (rows * cols/32 must be < 2^32)");
-    life_tb_kernel<K><<<(unsigned)blocks, TB_THREADS, 0, st>>>(in, out, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks);
+    if (HALO) {
+        // every rank has the same geometry, so my neighbours' strip counts equal mine: the upper
+        // neighbour signals me once per strip that pushed ITS bottom rows, the lower one per top strip
+        const uint32_t top = strips_touching(halo.store_lo, halo.store_lo + halo.depth, rpt, rows) * n_cgroups;
+        const uint32_t bot = strips_touching(halo.store_hi - halo.depth, halo.store_hi, rpt, rows) * n_cgroups;
+        halo.wait_up_target = (block_index - 1) * bot;
+        halo.wait_dn_target = (block_index - 1) * top;
+    }
+    life_tb_kernel<K, HALO><<<(unsigned)blocks, TB_THREADS, 0, st>>>(in, out, rows, W, rpt, wrap_rows, n_cgroups,
+                                                                   n_rblocks, halo);
     CGL_LAUNCH_CHECK();
     return 0;
 }
 
+template <bool HALO>
 static int tb_dispatch(int k, const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t cols, int wrap_rows,
-                       cudaStream_t st)
+                       cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0)
 {
+#define CGL_TB_CASE(KK) case KK: return launch_tb<KK, HALO>(in, out, rows, cols, wrap_rows, st, halo, block_index)
     switch (k) {
-        case 1: return launch_tb<1>(in, out, rows, cols, wrap_rows, st);
-        case 2: return launch_tb<2>(in, out, rows, cols, wrap_rows, st);
-        case 3: return launch_tb<3>(in, out, rows, cols, wrap_rows, st);
-        case 4: return launch_tb<4>(in, out, rows, cols, wrap_rows, st);
-        case 6: return launch_tb<6>(in, out, rows, cols, wrap_rows, st);
-        case 8: return launch_tb<8>(in, out, rows, cols, wrap_rows, st);
-        case 12: return launch_tb<12>(in, out, rows, cols, wrap_rows, st);
-        case 16: return launch_tb<16>(in, out, rows, cols, wrap_rows, st);
+        CGL_TB_CASE(1); CGL_TB_CASE(2); CGL_TB_CASE(3); CGL_TB_CASE(4);
+        CGL_TB_CASE(6); CGL_TB_CASE(8); CGL_TB_CASE(12); CGL_TB_CASE(16);
     }
+#undef CGL_TB_CASE
     set_error("cgl_life_run: no temporal-blocking kernel for k=%d", k);
     return CGL_E_BADARG;
 }
@@ -176,11 +306,85 @@ extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uin
         }
         int rc;
         if (step == 1) rc = cgl_life_step(src, dst, 1, rows, cols, wrap_rows, nullptr, stream);
-        else rc = tb_dispatch(step, src, dst, rows, cols, wrap_rows, st);
+        else rc = tb_dispatch<false>(step, src, dst, rows, cols, wrap_rows, st);
         if (rc) return rc;
         uint32_t *t = src; src = dst; dst = t;
         left -= (uint32_t)step;
     }
     if (result_in_a_out) *result_in_a_out = (src == buf_a) ? 1 : 0;
     return 0;
+}
+
+// Measure the strip length for this shape on the caller's buffers (buf_b is clobbered) and remember
+// the fastest; later cgl_life_run calls with the same (rows, cols, k) use it.  Synchronises the
+// stream; call it once at set-up, never inside a capture.
+extern "C" int cgl_life_tune(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uint32_t cols, int wrap_rows,
+                             uint32_t k, cgl_stream_t stream)
+{
+    CGL_REQUIRE(buf_a && buf_b && buf_a != buf_b && rows && cols, CGL_E_BADARG, "cgl_life_tune: bad argument");
+    if (!(cols % 32 == 0 && cols >= 32 * TB_COLS && rows >= 8) || k < 2) return 0;    // nothing to tune
+    int kk = 1;
+    for (int sz : {16, 12, 8, 6, 4, 3, 2})
+        if ((uint32_t)sz <= k) { kk = sz; break; }
+    const uint32_t W = cols / 32;
+    if (tuned_rows(rows, W, kk) != 0 || g_n_tuned >= 64) return 0;
+    cudaStream_t st = as_stream(stream);
+    cudaEvent_t e0, e1;
+    CGL_CUDA(cudaEventCreate(&e0));
+    CGL_CUDA(cudaEventCreate(&e1));
+    static const uint32_t cand[] = {96, 128, 160, 192, 224, 256, 320, 384, 512, 640, 768};
+    float best_ms = 1e30f;
+    uint32_t best = 0;
+    TunedRows &slot = g_tuned[g_n_tuned];
+    slot = TunedRows{rows, W, kk, 0};
+    ++g_n_tuned;                                   // visible to launch_tb through tuned_rows()
+    for (uint32_t rpt : cand) {
+        if (rpt < 8u * kk || rpt > rows) continue;
+        slot.rpt = rpt;
+        int rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st);      // warm-up
+        if (rc) return rc;
+        CGL_CUDA(cudaEventRecord(e0, st));
+        for (int rep = 0; rep < 2; ++rep)
+            if ((rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st))) return rc;
+        CGL_CUDA(cudaEventRecord(e1, st));
+        CGL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CGL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) { best_ms = ms; best = rpt; }
+    }
+    slot.rpt = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (best == 0) --g_n_tuned;
+    return 0;
+}
+
+// One band block: `gens` generations (a k with a kernel instance: 1,2,3,4,6,8,12,16; gens <= ghost) of a
+// row band that carries `ghost` ghost rows above and below its owned rows, fused with the halo
+// exchange for the NEXT block (see HaloCtx).  in/out: this rank's band buffers (buf_rows x cols);
+// peer_*_out: the ring neighbours' OUTPUT buffers of the same block (peer-mapped); peer_*_sig: their
+// arrival counters {from_above, from_below}; my_ctr: my own two counters; block_index: 1, 2, ...
+extern "C" int cgl_life_band_block(const uint32_t *in, uint32_t *out, uint32_t buf_rows, uint32_t cols,
+                                   uint32_t ghost, uint32_t gens, uint32_t *peer_up_out, uint32_t *peer_dn_out,
+                                   uint32_t *peer_up_ctr, uint32_t *peer_dn_ctr, const uint32_t *my_ctr,
+                                   uint32_t block_index, cgl_stream_t stream)
+{
+    CGL_REQUIRE(in && out && in != out && peer_up_out && peer_dn_out && peer_up_ctr && peer_dn_ctr && my_ctr,
+                CGL_E_BADARG, "cgl_life_band_block: null pointer");
+    CGL_REQUIRE(cols % 32 == 0 && cols >= 32 * TB_COLS && ghost >= 1 && gens >= 1 && gens <= ghost &&
+                buf_rows > 4 * ghost && block_index >= 1, CGL_E_BADARG, "cgl_life_band_block: bad shape");
+    const uint32_t W = cols / 32;
+    HaloCtx hc;
+    hc.store_lo = ghost;
+    hc.store_hi = buf_rows - ghost;
+    hc.depth = ghost;
+    // my first owned rows -> the upper neighbour's bottom ghost rows; my last owned rows -> the lower one's top ghosts
+    hc.push_up = peer_up_out + (uint64_t)(buf_rows - ghost) * W;
+    hc.push_dn = peer_dn_out;
+    hc.sig_up = peer_up_ctr + 1;          // I am the upper neighbour's "from below"
+    hc.sig_dn = peer_dn_ctr + 0;          // and the lower neighbour's "from above"
+    hc.wait_up = my_ctr + 0;
+    hc.wait_dn = my_ctr + 1;
+    hc.wait_up_target = hc.wait_dn_target = 0;
+    return tb_dispatch<true>((int)gens, in, out, buf_rows, cols, 0, as_stream(stream), hc, block_index);
 }

@@ -108,6 +108,12 @@ int cgl_life_run(uint32_t *buf_a_dev, uint32_t *buf_b_dev, uint32_t rows, uint32
                  int wrap_rows, uint32_t gens, uint32_t k, int *result_in_a_out,
                  cgl_stream_t stream);
 
+/* Optional set-up call: time a few strip lengths of the k-blocked kernel for this (rows, cols, k)
+ * on the caller's buffers (buf_b is clobbered, buf_a untouched) and remember the fastest for later
+ * cgl_life_run calls.  Synchronises the stream. */
+int cgl_life_tune(uint32_t *buf_a_dev, uint32_t *buf_b_dev, uint32_t rows, uint32_t cols, int wrap_rows,
+                  uint32_t k, cgl_stream_t stream);
+
 /* ---- reductions ----------------------------------------------------------------------------
  * reward(): np.add.reduce(stable, dtype=int32), CGL/CGL.py:255-256 (wraps mod 2^32).
  * alive():  np.add.reduce(world, dtype=uint32), CGL/CGL.py:259-260. */
@@ -149,13 +155,36 @@ int cgl_halo_push(const uint32_t *src_dev, uint32_t *peer_dst_dev, uint64_t n_wo
                   uint32_t *peer_flag_dev, uint32_t seq, cgl_stream_t stream);
 /* Block the stream until *flag_dev >= seq (written by a peer GPU). */
 int cgl_halo_wait(const uint32_t *flag_dev, uint32_t seq, cgl_stream_t stream);
+/* The whole exchange of one rank in ONE launch (2 CTAs: one per ring neighbour): push my top rows
+ * to the upper neighbour's landing slot and my bottom rows to the lower one's, publish `seq`, wait
+ * for their strips of the same block and move them into my ghost rows. */
+int cgl_halo_exchange(const uint32_t *top_src_dev, const uint32_t *bot_src_dev, uint32_t *peer_up_landing,
+                      uint32_t *peer_dn_landing, uint32_t *peer_up_flag, uint32_t *peer_dn_flag,
+                      const uint32_t *my_landing_up, const uint32_t *my_landing_dn, const uint32_t *my_flag_up,
+                      const uint32_t *my_flag_dn, uint32_t *ghost_up_dev, uint32_t *ghost_dn_dev,
+                      uint64_t n_words, uint32_t seq, cgl_stream_t stream);
 /* Same wait, then copy n_words from the landing zone `src_dev` into the ghost rows `dst_dev`. */
 int cgl_halo_wait_copy(const uint32_t *flag_dev, uint32_t seq, const uint32_t *src_dev, uint32_t *dst_dev,
                        uint64_t n_words, cgl_stream_t stream);
+/* One row-band block with the halo exchange FUSED into the generation kernel (multi-GPU life mode).
+ * The band buffer holds `ghost` ghost rows, the owned rows, `ghost` ghost rows.  Runs `gens`
+ * (<= ghost; 1,2,3,4,6,8,12 or 16) generations in -> out in one launch; the kernel writes this
+ * rank's first/last `ghost` owned rows straight into the ring neighbours' OUTPUT buffers
+ * (peer_up_out / peer_dn_out: CUDA-IPC mapped, same layout) and bumps their arrival counters
+ * (peer_*_ctr: uint32[2] = {from_above, from_below}); strips that read ghost rows first wait on
+ * my_ctr until both neighbours completed block_index - 1.  block_index = 1 for the first block after
+ * the ghosts were filled by a plain exchange (counters zeroed), then 2, 3, ...  No extra launch, no
+ * host synchronisation, interior strips never wait. */
+int cgl_life_band_block(const uint32_t *in_dev, uint32_t *out_dev, uint32_t buf_rows, uint32_t cols,
+                        uint32_t ghost, uint32_t gens, uint32_t *peer_up_out, uint32_t *peer_dn_out,
+                        uint32_t *peer_up_ctr, uint32_t *peer_dn_ctr, const uint32_t *my_ctr,
+                        uint32_t block_index, cgl_stream_t stream);
+
 /* Plain cudaMalloc'ed (zero-filled) device memory: IPC handles need whole allocations, which
  * a caching allocator's sub-blocks are not. */
 int cgl_dev_alloc(uint64_t bytes, void **dev_ptr_out);
 int cgl_dev_free(void *dev_ptr);
+int cgl_dev_memset(void *dev_ptr, int value, uint64_t bytes, cgl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,7 @@ def test_randomize_is_partition_invariant(bands):
     assert torch.equal(torch.cat(parts, 0), a.owned)
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "dist"])
+@pytest.mark.parametrize("exchange", ["fused", "p2p", "dist"])
 def test_two_gpu_bands_match_single_gpu(bands, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

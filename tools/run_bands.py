@@ -24,7 +24,7 @@ ap.add_argument("--cols", type=int, default=65536)
 ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--gens", type=int, default=1000)
 ap.add_argument("--warmup", type=int, default=16)
-ap.add_argument("--exchange", default="p2p", choices=["p2p", "dist"])
+ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "dist"])
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--seed", type=int, default=1)
 a = ap.parse_args()
