@@ -54,12 +54,16 @@ class _null:
 
 class RowBandLife:
     def __init__(self, rows: int, cols: int, k: int = 8, rank: int = 0, world_size: int = 1, device="cuda",
-                 exchange: str | None = None, group=None, lib=None):
+                 exchange: str | None = None, group=None, lib=None, kernel_k: int | None = None):
+        """k = ghost depth = generations between halo exchanges; kernel_k = generations per launch
+        (temporal-blocking depth, default min(k, 8)): k = 16, kernel_k = 8 exchanges every 16
+        generations and runs two 8-generation launches in between."""
         if rows % world_size:
             raise ValueError("rows must be divisible by world_size")
         if cols % 32:
             raise ValueError("cols must be a multiple of 32 for row bands")
         self.rows, self.cols, self.k = rows, cols, int(k)
+        self.kernel_k = int(kernel_k) if kernel_k else min(self.k, 8)
         self.rank, self.G = rank, world_size
         self.W = cols // 32
         self.band_rows = rows // world_size
@@ -253,13 +257,13 @@ class RowBandLife:
             with torch.cuda.device(self.device):
                 native.check(lib.cgl_life_tune(native.dptr(self._a), native.dptr(self._b),
                                                self.band_rows if self.G == 1 else self.buf_rows, self.cols,
-                                               1 if self.G == 1 else 0, self.k, st), "cgl_life_tune")
+                                               1 if self.G == 1 else 0, self.kernel_k, st), "cgl_life_tune")
             self._tuned = True
         if self.G == 1:                      # plain torus: one call, k generations per launch
             with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
-                if not _life_block(lib, self._a, self._b, self.band_rows, self.cols, 1, gens, self.k, st):
+                if not _life_block(lib, self._a, self._b, self.band_rows, self.cols, 1, gens, self.kernel_k, st):
                     self._a, self._b = self._b, self._a
-            self.launches += -(-gens // self.k)
+            self.launches += -(-gens // self.kernel_k)
             self.generation += gens
             return
         if self.exchange == "fused":
@@ -269,9 +273,9 @@ class RowBandLife:
             kb = min(self.k, gens - done)
             self._exchange()
             with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
-                if not _life_block(lib, self._a, self._b, self.buf_rows, self.cols, 0, kb, kb, st):
+                if not _life_block(lib, self._a, self._b, self.buf_rows, self.cols, 0, kb, min(kb, self.kernel_k), st):
                     self._a, self._b = self._b, self._a
-            self.launches += 1
+            self.launches += -(-kb // self.kernel_k)
             done += kb
             self.generation += kb
 

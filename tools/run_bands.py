@@ -23,6 +23,7 @@ ap.add_argument("--rows", type=int, default=65536)
 ap.add_argument("--cols", type=int, default=65536)
 ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--gens", type=int, default=1000)
+ap.add_argument("--kernel-k", type=int, default=0, help="generations per launch (default min(k, 8))")
 ap.add_argument("--warmup", type=int, default=16)
 ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "dist"])
 ap.add_argument("--check", action="store_true")
@@ -36,7 +37,8 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
 
-band = RowBandLife(a.rows, a.cols, k=a.k, rank=rank, world_size=world, device=dev, exchange=a.exchange if world > 1 else None)
+band = RowBandLife(a.rows, a.cols, k=a.k, rank=rank, world_size=world, device=dev, exchange=a.exchange if world > 1 else None,
+                   kernel_k=a.kernel_k or None)
 band.randomize(a.seed)
 result = {"rows": a.rows, "cols": a.cols, "k": a.k, "gens": a.gens, "n_gpus": world, "exchange": band.exchange}
 if a.check:
