@@ -223,15 +223,25 @@ class BatchedSim:
         """The same step driven from HOST buffers: actions int32 [B] (pinned) are copied H2D, the
         step runs, reward int32 [B] (and the int8 observation if obs_host is given) come back D2H;
         returns after the copies completed.  One C-ABI call: cgl_env_step_host."""
-        if not hasattr(self, "_act_dev"):
-            self._act_dev = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            rc = self._lib.cgl_env_step_host(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                             self.n_envs, self.side, native.dptr(actions_host),
-                                             native.dptr(self._act_dev), self.spawn, self.stable_max,
-                                             native.dptr(self._reward), native.dptr(reward_host),
-                                             native.dptr(obs_host), self._stream())
-        native.check(rc, "cgl_env_step_host")
+        key = (0 if actions_host is None else actions_host.data_ptr(), reward_host.data_ptr(),
+               0 if obs_host is None else obs_host.data_ptr(), self._wa.data_ptr())
+        args = self._host_args.get(key) if hasattr(self, "_host_args") else None
+        if args is None:                                    # ctypes argument tuples are built once per buffer set
+            if not hasattr(self, "_act_dev"):
+                self._act_dev = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+                self._host_args = {}
+                self._n_launch_host = {}
+            V = ctypes.c_void_p
+            args = (V(self._wa.data_ptr()), V(self._wb.data_ptr()), V(self.stable.data_ptr()), self.n_envs, self.side,
+                    native.dptr(actions_host), V(self._act_dev.data_ptr()), self.spawn, self.stable_max,
+                    V(self._reward.data_ptr()), native.dptr(reward_host), native.dptr(obs_host))
+            self._host_args[key] = args
+            self._n_launch_host[key] = self._lib.cgl_env_step_launches(self.side, int(actions_host is not None))
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
+        rc = self._lib.cgl_env_step_host(*args, self._stream())
+        if rc:
+            native.check(rc, "cgl_env_step_host")
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
-        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_host is not None))
+        self.launches += self._n_launch_host[key]

@@ -200,10 +200,24 @@ extern "C" int cgl_env_step_host(uint32_t *win, uint32_t *wout, int8_t *stable, 
     cudaStream_t st = as_stream(stream);
     if (actions_host)
         CGL_CUDA(cudaMemcpyAsync(actions_dev, actions_host, n_envs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // Pinned (device-mapped) reward buffer: the kernel writes the per-env rewards straight into host
+    // memory (posted PCIe writes, 4 B per env) instead of a separate device-to-host copy.
+    int32_t *reward_target = reward_host ? reward_dev : nullptr;
+    bool reward_direct = false;
+    if (reward_host) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, reward_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr) {
+            reward_target = static_cast<int32_t *>(attr.devicePointer);
+            reward_direct = true;
+        } else {
+            cudaGetLastError();          // pageable memory: clear the sticky "invalid value" and copy instead
+        }
+    }
     int rc = cgl_env_step(win, wout, stable, n_envs, side, actions_host ? actions_dev : nullptr, spawn,
-                          stable_max, reward_host ? reward_dev : nullptr, nullptr, nullptr, stream);
+                          stable_max, reward_target, nullptr, nullptr, stream);
     if (rc) return rc;
-    if (reward_host)
+    if (reward_host && !reward_direct)
         CGL_CUDA(cudaMemcpyAsync(reward_host, reward_dev, n_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (obs_host)
         CGL_CUDA(cudaMemcpyAsync(obs_host, stable, n_envs * (uint64_t)side * side, cudaMemcpyDeviceToHost, st));
