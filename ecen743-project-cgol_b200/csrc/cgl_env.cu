@@ -112,6 +112,13 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     const uint32_t e = blockIdx.x * C::EPC + g;
     const bool active = e < n_envs;
 
+    // Programmatic dependent launch: the NEXT launch's CTAs may take the SM slots this grid frees in
+    // its tail (hides the launch latency between back-to-back steps); they wait here until this grid
+    // has completed.  The stability loads stay the first thing a CTA does after that -- a CTA's
+    // life is latency-bound, and the mask-table fill below overlaps with those loads.
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+
     // ---- phase 0: stability loads in flight before anything else --------------------------
     uint4 *sp = reinterpret_cast<uint4 *>(stable + (size_t)e * C::SIZE);
     uint4 sreg[C::UNR];
@@ -252,6 +259,17 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     }
 }
 
+// CGL_ENV_PDL=0 turns programmatic dependent launch off (tuning / debugging).
+static bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CGL_ENV_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <int S>
 static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             const int32_t *actions, int spawn, int stable_max, int32_t *reward,
@@ -266,10 +284,18 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
         CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM + pad));
     }
-    env_step_fused_kernel<S><<<grid, C::THREADS, C::SMEM + pad, st>>>(
-        win, wout, stable, (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive,
-        err);
-    CGL_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM + pad;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S>, win, wout, stable, (uint32_t)n_envs, actions,
+                                rep4(spawn), rep4(stable_max), reward, alive, err));
     return 0;
 }
 
