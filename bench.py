@@ -382,6 +382,34 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
     del band
     torch.cuda.empty_cache()
     if world == 1:
+        # C1: the reference's own single-env loop shape (CGL/main.py:64-72 with random actions) through the
+        # drop-in facade, 64x64; beside it the oracle port running the same loop on one host core
+        import CGL
+        from oracle import oracle
+        side, n = 64, 2000
+        acts = np.random.RandomState(123).randint(side * side + 1, size=n + 100).astype(np.int32)
+        env = CGL.sim(side=side, seed=0, gpu=True, gpu_select=dev.index, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE)
+        obs = env.get_stable(vector=True, shallow=True)
+        acc = 0
+        for i in range(100):
+            env.toggle_state(acts[i]); env.step(); obs = env.get_stable(vector=True, shallow=True); acc += int(env.reward())
+        t0 = time.perf_counter()
+        for i in range(100, 100 + n):
+            env.toggle_state(acts[i]); env.step(); obs = env.get_stable(vector=True, shallow=True); acc += int(env.reward())
+        dt_f = time.perf_counter() - t0
+        ref = oracle.OracleSim(side=side, seed=0, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE)
+        acc_o = 0
+        for i in range(100):
+            ref.toggle_state(acts[i]); ref.step(); acc_o += int(ref.reward())
+        t0 = time.perf_counter()
+        for i in range(100, 100 + n):
+            ref.toggle_state(acts[i]); ref.step(); acc_o += int(ref.reward())
+        dt_o = time.perf_counter() - t0
+        out["c1_single_64x64_loop"] = {"facade_env_steps_per_s": n / dt_f, "oracle_port_1core_env_steps_per_s": n / dt_o,
+                                       "reference_python_env_steps_per_s": 76.0,
+                                       "reference_source": "BASELINE.md section 2 (measured in the survey container)",
+                                       "rewards_equal": acc == acc_o}
+        del env
         # C5: 32768^2 torus, sweep of the temporal-blocking depth k on one GPU
         n = 32768
         words = n * (n // 32)

@@ -19,7 +19,9 @@ Deliberate deviations (all documented in DESIGN.md section 2):
     non-square sizes flow into its arithmetic unchecked, SURVEY.md N4) -> ValueError here;
   * shallow views are pinned host mirrors kept up to date by every state-changing call
     (reads see live state, aliasing `state is n_state` holds, CGL/main.py:60,70); writes INTO a
-    shallow view do not reach the device -- use toggle_state / update_state / load.
+    shallow view do not reach the device -- use toggle_state / update_state / load;
+  * a single-index toggle_state is applied lazily: it is fused into the next step() launch, or applied
+    by the next other call into the env; a shallow view shows it from that call on.
 """
 from __future__ import annotations
 
@@ -154,6 +156,22 @@ class sim:
         self._m_stable = self._m_stable_t.numpy()
         self._world_fresh = self._stable_fresh = False
         self._world_live = self._stable_live = False       # a shallow view has been handed out
+        # one pinned word each for the fused step: the kernel reads the pending action from and writes
+        # the reward to device-mapped host memory -- a step is ONE launch without staging copies
+        self._m_action_t = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._m_reward_t = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._m_action, self._m_reward = self._m_action_t.numpy(), self._m_reward_t.numpy()
+        self._pending = None                                # scalar toggle deferred into the next step()
+        self._reward_valid = False                          # _m_reward holds reward() of the current state
+
+    def _flush(self):
+        """Apply a deferred scalar toggle now (anything that observes the state between toggle_state and
+        step must see it)."""
+        if self._pending is not None:
+            a, self._pending = self._pending, None
+            self._b.toggle(self._torch.tensor([[a]], dtype=self._torch.int32, device=self._dev))
+            self._reward_valid = False
+            self._changed()
 
     def _changed(self, world=True, stable=True):
         """Device state changed: invalidate mirrors, eagerly refresh the ones with live views."""
@@ -181,11 +199,13 @@ class sim:
     # reference attribute names (read access): live host views of the device state
     @property
     def world(self):
+        self._flush()
         self._world_live = True
         return self._sync_world()
 
     @property
     def stable(self):
+        self._flush()
         self._stable_live = True
         return self._sync_stable()
 
@@ -208,24 +228,45 @@ class sim:
         if forceCPU:
             raise RuntimeError("forceCPU is not available in the B200 build (no CPU step); use the reference for that")
         self.count += 1
-        self._b.step(None)
+        # toggle (if one is pending) + generation + stability + reward in one launch; the action word is
+        # read from, and the reward written to, pinned host memory
+        actions_ptr = 0
+        if self._pending is not None:
+            self._m_action[0] = self._pending
+            self._pending = None
+            actions_ptr = self._m_action_t.data_ptr()
+        with self._torch.cuda.device(self._dev):
+            if self._b.fused:       # one thread per env writes the reward: straight into the pinned word
+                self._b.step_ptrs(actions_ptr, self._m_reward_t.data_ptr())
+            else:                   # generic kernels accumulate it with atomics: keep those on the device
+                self._b.step_ptrs(actions_ptr, self._b._reward.data_ptr())
+                self._m_reward_t.copy_(self._b._reward, non_blocking=True)
+        self._reward_valid = True
         self._changed()
 
     def reward(self):
         """np.int32 sum of the stability vector (CGL/CGL.py:255-256)."""
+        self._flush()
+        if self._reward_valid:                              # written by the last step's kernel
+            self._torch.cuda.current_stream(self._dev).synchronize()
+            return np.int32(self._m_reward[0])
         return np.int32(self._b.reward().item())
 
     def alive(self):
         """np.uint32 number of live cells (CGL/CGL.py:259-260)."""
+        self._flush()
         return np.uint32(self._b.alive().item())
 
     def reset(self):
         """Back to the initial state; `count` is not reset (CGL/CGL.py:264-266)."""
+        self._pending = None
+        self._reward_valid = False
         self._b.reset()
         self._changed()
 
     def match(self, terminalState):
         """(world == terminalState.flatten()).all()  (CGL/CGL.py:269-270)."""
+        self._flush()
         flat = np.asarray(terminalState).flatten()
         if flat.size != self.size:
             raise ValueError(f"terminalState has {flat.size} cells, expected {self.size}")
@@ -236,6 +277,7 @@ class sim:
     # ------------------------------------------------------------------------------ I/O
     def get_state(self, vector=False, shallow=False):
         """World as uint8 vector or (side, side) matrix (CGL/CGL.py:274-278)."""
+        self._flush()
         if shallow:
             self._world_live = True
         w = self._sync_world()
@@ -244,6 +286,7 @@ class sim:
 
     def get_stable(self, vector=False, shallow=False):
         """Stability (the observation) as int8 vector or matrix (CGL/CGL.py:281-285)."""
+        self._flush()
         if shallow:
             self._stable_live = True
         s = self._sync_stable()
@@ -275,6 +318,7 @@ class sim:
             raise ValueError("The new state must have the same size and side as the original state!\n"
                              f"Was given size={temp.size} and side={side} but was expecting size={self.size} and side={self.side}.")
         cells = self._validated_cells(temp)
+        self._flush()
         self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
         self._changed(world=True, stable=False)
 
@@ -287,8 +331,16 @@ class sim:
             if indx.dtype.kind not in "iu":
                 raise IndexError("arrays used as indices must be of integer (or boolean) type")
             flat = np.ascontiguousarray(indx.reshape(-1), dtype=np.int32)
-            if flat.size:
+            self._flush()                                   # an earlier deferred toggle goes first
+            if flat.size == 1:
+                # the DQN loop's case (CGL/main.py:66-67): one index, then step() -- deferred and fused
+                # into that launch.  Every other call into the env applies it first (_flush), so the
+                # only place it is not yet visible is a shallow numpy view read before the next call.
+                self._pending = int(flat[0])
+                self._reward_valid = False
+            elif flat.size:
                 self._b.toggle(self._torch.from_numpy(flat).to(self._dev)[None, :])
+                self._reward_valid = False
                 self._changed()
         elif indx != self.size:     # an array with >1 element raises ValueError here, like the reference
             raise ValueError("Not all indexes are valid!\nIndexes must be positive and less than the size of the "
@@ -296,6 +348,7 @@ class sim:
 
     def save(self):
         """(world, stable, side, count, spawn, stable_max) -- host copies (CGL/CGL.py:332-333)."""
+        self._flush()
         return (np.copy(self._sync_world()), np.copy(self._sync_stable()), self.side, self.count,
                 self.spawnStabilityFactor, self.stableStabilityFactor)
 
@@ -318,6 +371,8 @@ class sim:
         if cells.size != side * side or stab.size != side * side:
             raise ValueError(f"newState/newstable must have side*side = {side * side} cells")
         from cgl_b200.batched import BatchedSim
+        self._pending = None
+        self._reward_valid = False
         self.stableStabilityFactor = stableStabilityFactor
         self.spawnStabilityFactor = spawnStabilityFactor
         resized = side != self.side

@@ -150,6 +150,20 @@ class BatchedSim:
         done = self._done[self.max_steps is not None and self.count >= self.max_steps]
         return self.stable, self._reward, done
 
+    def step_ptrs(self, actions_ptr: int, reward_ptr: int) -> None:
+        """step() with raw pointers: `actions_ptr` (0 = no actions) and `reward_ptr` may be device memory
+        or device-mapped pinned host memory -- the single-env facade passes pinned words so that a step is
+        one launch with no staging copies."""
+        rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                    self.n_envs, self.side, ctypes.c_void_p(actions_ptr), self.spawn,
+                                    self.stable_max, ctypes.c_void_p(reward_ptr), None, native.dptr(self._err),
+                                    self._stream())
+        if rc:
+            native.check(rc, "cgl_env_step")
+        self._wa, self._wb = self._wb, self._wa
+        self.count += 1
+        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_ptr != 0))
+
     def check_actions(self) -> None:
         """Synchronise and raise ValueError if any action since the last check was outside
         [0, size] (the reference raises at toggle time, CGL/CGL.py:327-328)."""
