@@ -343,3 +343,43 @@ def test_temporal_blocking_open_band_interior(cgl, rows, cols, k):
     padded[k + 1:k + 1 + rows] = cells
     want = oracle.life(padded, k, threads=4)[k + 1:k + 1 + rows]
     assert np.array_equal(got[k:rows - k], want[k:rows - k])
+
+
+# ------------------------------------------------------------------------------------------
+# opt-in kernel variants stay parity-green (selected by environment knobs, so run in a subprocess)
+# ------------------------------------------------------------------------------------------
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+from cgl_b200.batched import BatchedSim
+from oracle import oracle
+for side, n in ((128, 9), (64, 37), (32, 70)):
+    size = side * side
+    rs = np.random.RandomState(side)
+    cells = rs.randint(2, size=(n, size)).astype(np.uint8)
+    st = rs.randint(-128, 128, size=(n, size)).astype(np.int8)
+    env = BatchedSim(n, side, spawnStabilityFactor=-2, stableStabilityFactor=2, states=cells)
+    env.stable.copy_(torch.from_numpy(st))
+    for _ in range(3):
+        acts = rs.randint(size + 1, size=n).astype(np.int32)
+        rew_o, alv_o = oracle.step_batch(cells, st, side, acts, -2, 2, threads=4)
+        obs, rew, _ = env.step(torch.from_numpy(acts).cuda(), want_alive=True)
+        assert np.array_equal(env.get_state().cpu().numpy(), cells)
+        assert np.array_equal(obs.cpu().numpy(), st)
+        assert np.array_equal(rew.cpu().numpy(), rew_o)
+        assert np.array_equal(env.last_alive().cpu().numpy(), alv_o.astype(np.int64))
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("knobs", [{"CGL_ENV_IMPL": "tma", "CGL_ENV_TMA_THREADS": "256"},
+                                   {"CGL_ENV_IMPL": "tma", "CGL_ENV_TMA_THREADS": "128"},
+                                   {"CGL_ENV_PDL": "0"}])
+def test_env_kernel_variants_vs_oracle(cgl, knobs):
+    """The persistent bulk-copy (cp.async.bulk + mbarrier) kernel and the non-PDL launch path."""
+    import subprocess
+    import sys
+    from conftest import PKG
+    env = dict(os.environ, **knobs)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, ROOT, PKG], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
