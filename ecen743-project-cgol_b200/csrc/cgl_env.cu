@@ -124,7 +124,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     uint4 sreg[C::UNR];
     if (active) {
 #pragma unroll
-        for (int u = 0; u < C::UNR; ++u) sreg[u] = sp[t + u * C::TPE];
+        for (int u = 0; u < C::UNR; ++u) sreg[u] = (sp + t)[u * C::TPE];
     }
 
     for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
@@ -208,28 +208,36 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         const uint32_t act_mask = 0xffu << ((act & 3) * 8);
         const uint32_t tbn = ((tb >> 8) & 0xffu) * 0x01010101u;   // table-base byte under every nibble
         const uint32_t lane_s = (threadIdx.x & 31) * 4, lane_b = lane_s + 128;
+        uint4 *spt = sp + t;                          // this thread's chunks: spt[u * TPE] (immediate offsets)
+        const uint32_t *mixt = mix + t;
+        const uint32_t keep = ~act_mask, put = spawn4 & act_mask;
+        // the thread that owns the action's chunk patches it once, outside the unrolled chunk loop
+        auto patch = [&](uint4 &v) {
+            if (act_sub == 0) v.x = (v.x & keep) | put;
+            else if (act_sub == 1) v.y = (v.y & keep) | put;
+            else if (act_sub == 2) v.z = (v.z & keep) | put;
+            else v.w = (v.w & keep) | put;
+        };
+        if (t == act_t && act_u >= 0 && act_u < C::UNR) {
+#pragma unroll
+            for (int u = 0; u < C::UNR; ++u)
+                if (act_u == u) patch(sreg[u]);
+        }
 #pragma unroll
         for (int b0 = 0; b0 < C::CPT; b0 += C::UNR) {
             if (b0 > 0) {
 #pragma unroll
                 for (int u = 0; u < C::UNR; ++u)
-                    if (b0 + u < C::CPT) sreg[u] = sp[t + (b0 + u) * C::TPE];
+                    if (b0 + u < C::CPT) {
+                        sreg[u] = spt[(b0 + u) * C::TPE];
+                        if (act_u == b0 + u && t == act_t) patch(sreg[u]);
+                    }
             }
 #pragma unroll
             for (int u = 0; u < C::UNR; ++u) {
                 if (b0 + u >= C::CPT) continue;
-                const int q = t + (b0 + u) * C::TPE;
-                if (act_u == b0 + u) {
-                    if (t == act_t) {
-                        const uint32_t keep = ~act_mask, put = spawn4 & act_mask;
-                        if (act_sub == 0) sreg[u].x = (sreg[u].x & keep) | put;
-                        else if (act_sub == 1) sreg[u].y = (sreg[u].y & keep) | put;
-                        else if (act_sub == 2) sreg[u].z = (sreg[u].z & keep) | put;
-                        else sreg[u].w = (sreg[u].w & keep) | put;
-                    }
-                }
                 uint32_t s[4] = {sreg[u].x, sreg[u].y, sreg[u].z, sreg[u].w};
-                const uint32_t m = mix[q];
+                const uint32_t m = mixt[(b0 + u) * C::TPE];
                 const uint32_t sv = (m & 0x0f0f0f0fu) | tbn;
                 const uint32_t bn = ((m >> 4) & 0x0f0f0f0fu) | tbn;
 #pragma unroll
@@ -240,7 +248,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                     s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
                     acc = __dp4a((int)s[k], 0x01010101, acc);
                 }
-                sp[q] = make_uint4(s[0], s[1], s[2], s[3]);
+                spt[(b0 + u) * C::TPE] = make_uint4(s[0], s[1], s[2], s[3]);
             }
         }
     }

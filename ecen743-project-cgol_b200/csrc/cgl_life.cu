@@ -168,7 +168,12 @@ extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs,
     cudaStream_t st = as_stream(stream);
     const uint32_t W = cols / 32, W4 = W / 4;
     const uint32_t n_cgroups = (W4 + 31) / 32;
-    const uint32_t rpt = pick_rows_per_strip(n_envs, rows, n_cgroups);
+    static int rows_knob = -1;                   // CGL_LIFE_ROWS overrides the strip length (tuning; multiple of 6)
+    if (rows_knob < 0) {
+        const char *v = getenv("CGL_LIFE_ROWS");
+        rows_knob = v ? atoi(v) : 0;
+    }
+    const uint32_t rpt = rows_knob > 0 ? (uint32_t)rows_knob : pick_rows_per_strip(n_envs, rows, n_cgroups);
     const uint32_t n_rblocks = (rows + rpt - 1) / rpt;
     const uint64_t warps = n_envs * n_cgroups * n_rblocks;
     const uint64_t blocks = (warps + (LIFE_ROWS_THREADS / 32) - 1) / (LIFE_ROWS_THREADS / 32);

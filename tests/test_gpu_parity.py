@@ -383,3 +383,23 @@ def test_env_kernel_variants_vs_oracle(cgl, knobs):
     env = dict(os.environ, **knobs)
     r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, ROOT, PKG], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_facade_reference_attributes(cgl):
+    """Attribute names scripts of the reference touch directly (world, stable, initState, initStable, ...)."""
+    tr = TRACES["tiny10"]
+    env = cgl.sim(state=tr.worlds[0].reshape(10, 10), gpu=True, spawnStabilityFactor=tr.spawn,
+                  stableStabilityFactor=tr.stable_max)
+    assert np.array_equal(env.world, tr.worlds[0]) and np.array_equal(env.stable, tr.stables[0])
+    assert np.array_equal(env.initState, tr.worlds[0]) and np.array_equal(env.initStable, tr.stables[0])
+    assert (env.size, env.side, env.count, env.gpu) == (100, 10, 0, True)
+    env.toggle_state(np.int32(tr.action(0)))
+    assert env.reward() == tr.rewards_after_toggle[0]          # deferred toggle is visible to reward()
+    env.step()
+    assert np.array_equal(env.world, tr.worlds[1]) and np.array_equal(env.stable, tr.stables[1])
+    assert np.array_equal(env.initState, tr.worlds[0])         # reset source untouched
+    env.toggle_state(np.int32(tr.action(1)))
+    env.toggle_state(np.int32(tr.action(1)))                   # two deferred toggles of one cell cancel in the world ...
+    w = env.get_state(vector=True)
+    assert np.array_equal(w, tr.worlds[1])
+    assert env.get_stable(vector=True)[tr.action(1)] == tr.spawn or tr.action(1) == 100   # ... but stable = spawn
