@@ -16,6 +16,7 @@ do not depend on the number of GPUs.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,18 @@ class BatchedSim:
             self._reward = torch.zeros(B, dtype=torch.int32, device=self.device)
             self._alive = torch.zeros(B, dtype=torch.int32, device=self.device)   # uint32 bits
             self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # per-env tokens of the chained fused step (cgl_env_step_chained): token[e] = id of the plane
+            # that holds env e's latest world (1 = first plane, 2 = second); _token_plane = the plane
+            # (data_ptr) all tokens currently name, None = stale (set again before the next chained step)
+            self._tokens = torch.zeros(B, dtype=torch.int32, device=self.device) if self.fused else None
+            self._plane_id = {self._wa.data_ptr(): 1, self._wb.data_ptr(): 2}
+            self._token_plane = None
+            # Chaining pays when a launch is only a few waves of CTAs deep (its tail is a large share of
+            # it): measured on B200, +9 % at 4096 CTAs (C2), -7 % at 16384 CTAs (the token check adds a
+            # dependent load to every CTA).  CGL_ENV_CHAINED=0/1 forces it off/on.
+            n_ctas = -(-B // max(1, 128 // max(32, side if side > 64 else 32)))
+            force = os.environ.get("CGL_ENV_CHAINED")
+            self.chained = self.fused and (force == "1" or (force != "0" and 2400 < n_ctas <= 8192))
             self._done = {False: torch.zeros(B, dtype=torch.bool, device=self.device),
                           True: torch.ones(B, dtype=torch.bool, device=self.device)}
             if states is not None:
@@ -138,11 +151,23 @@ class BatchedSim:
                 raise TypeError("actions must be an int32 CUDA tensor with one entry per env")
             actions = actions.contiguous()
         with torch.cuda.device(self.device):
-            rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                        self.n_envs, self.side, native.dptr(actions), self.spawn,
-                                        self.stable_max, native.dptr(self._reward),
-                                        native.dptr(self._alive) if want_alive else None,
-                                        native.dptr(self._err), self._stream())
+            if self.chained:        # per-env dependency between consecutive launches (see the C header)
+                src, dst = self._wa.data_ptr(), self._wb.data_ptr()
+                if self._token_plane != src:        # first chained step, or a non-chained op swapped the planes
+                    self._tokens.fill_(self._plane_id[src])
+                rc = self._lib.cgl_env_step_chained(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                                    self.n_envs, self.side, native.dptr(actions), self.spawn,
+                                                    self.stable_max, native.dptr(self._reward),
+                                                    native.dptr(self._alive) if want_alive else None,
+                                                    native.dptr(self._err), native.dptr(self._tokens),
+                                                    self._plane_id[src], self._plane_id[dst], self._stream())
+                self._token_plane = dst
+            else:
+                rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                            self.n_envs, self.side, native.dptr(actions), self.spawn,
+                                            self.stable_max, native.dptr(self._reward),
+                                            native.dptr(self._alive) if want_alive else None,
+                                            native.dptr(self._err), self._stream())
         native.check(rc, "cgl_env_step")
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
@@ -167,7 +192,11 @@ class BatchedSim:
     def check_actions(self) -> None:
         """Synchronise and raise ValueError if any action since the last check was outside
         [0, size] (the reference raises at toggle time, CGL/CGL.py:327-328)."""
-        if int(self._err.item()) != 0:
+        err = int(self._err.item())
+        if err & 2:
+            self._err.zero_()
+            raise native.CglNativeError("chained env step: a plane token never arrived (state planes out of sync)")
+        if err != 0:
             self._err.zero_()
             raise ValueError(f"Not all indexes are valid!\nIndexes must be positive and less than the size of the state {self.size}.")
 

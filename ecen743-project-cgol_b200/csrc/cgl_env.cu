@@ -91,7 +91,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                       int8_t *__restrict__ stable, uint32_t n_envs,
                       const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
-                      int *__restrict__ err_flag)
+                      int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish)
 {
     using C = EnvCfg<S>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -117,7 +117,30 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     // has completed.  The stability loads stay the first thing a CTA does after that -- a CTA's
     // life is latency-bound, and the mask-table fill below overlaps with those loads.
     cudaTriggerProgrammaticLaunchCompletion();
-    cudaGridDependencySynchronize();
+    if (epoch == nullptr) {
+        cudaGridDependencySynchronize();
+    } else {
+        // Chained steps: env e of this launch depends only on env e of the previous launch, which
+        // published epoch[e] = want (the id of the plane this launch reads) when it was done.  The
+        // next launch's first CTAs therefore start while the previous launch's last CTAs are still
+        // running (ramp-up overlaps the tail); the spin almost never iterates because CTAs are
+        // dispatched in env order.  The token load is issued first and the mask tables are filled in
+        // its shadow.  The spin is bounded: a token that never arrives (caller bug) raises bit 1 of
+        // the error flag instead of hanging the GPU.
+        uint32_t v = want;
+        if (t == 0 && active) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
+        for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
+            const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
+            tables[i] = (i & 32) ? (m & spawn4) : m;
+        }
+        if (t == 0 && active) {
+            uint32_t spins = 0;
+            while (v != want && ++spins < (1u << 22))
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
+            if (v != want && err_flag != nullptr) atomicOr(err_flag, 2);
+        }
+        __syncthreads();
+    }
 
     // ---- phase 0: stability loads in flight before anything else --------------------------
     uint4 *sp = reinterpret_cast<uint4 *>(stable + (size_t)e * C::SIZE);
@@ -127,9 +150,11 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         for (int u = 0; u < C::UNR; ++u) sreg[u] = (sp + t)[u * C::TPE];
     }
 
-    for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
-        const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
-        tables[i] = (i & 32) ? (m & spawn4) : m;
+    if (epoch == nullptr) {
+        for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
+            const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
+            tables[i] = (i & 32) ? (m & spawn4) : m;
+        }
     }
     if (t == 0) { red[0] = 0; red[1] = 0; }
 
@@ -252,6 +277,12 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             }
         }
     }
+    if (epoch != nullptr) {
+        // publish: barrier (all stores of this env issued), then ONE release store -- release is
+        // cumulative over what the barrier ordered before it (the grid-sync idiom)
+        __syncthreads();
+        if (t == 0 && active) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(epoch + e), "r"(publish) : "memory");
+    }
     if (reward_out != nullptr || alive_out != nullptr) {
         acc = __reduce_add_sync(0xffffffffu, acc);
         pop = __reduce_add_sync(0xffffffffu, pop);
@@ -281,7 +312,8 @@ static bool pdl_enabled()
 template <int S>
 static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             const int32_t *actions, int spawn, int stable_max, int32_t *reward,
-                            uint32_t *alive, int *err, cudaStream_t st)
+                            uint32_t *alive, int *err, cudaStream_t st, uint32_t *epoch = nullptr, uint32_t want = 0,
+                            uint32_t publish = 0)
 {
     using C = EnvCfg<S>;
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
@@ -303,7 +335,7 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S>, win, wout, stable, (uint32_t)n_envs, actions,
-                                rep4(spawn), rep4(stable_max), reward, alive, err));
+                                rep4(spawn), rep4(stable_max), reward, alive, err, epoch, want, publish));
     return 0;
 }
 
@@ -634,6 +666,29 @@ extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint6
         win, wout, stable, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward);
     CGL_LAUNCH_CHECK();
     return 0;
+}
+
+// Chained form of cgl_env_step for the fused sides: see include/cgl_b200.h.
+extern "C" int cgl_env_step_chained(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
+                                    const int32_t *actions, int spawn, int stable_max, int32_t *reward,
+                                    uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want,
+                                    uint32_t publish, cgl_stream_t stream)
+{
+    CGL_REQUIRE(win && wout && stable && n_envs && side && epoch_flags && win != wout, CGL_E_BADARG,
+                "cgl_env_step_chained: bad argument");
+    CGL_REQUIRE(cgl_env_step_is_fused(side) && n_envs < (1ull << 31), CGL_E_BADARG,
+                "cgl_env_step_chained: side must be a fused side (multiple of 32, 32..256)");
+    cudaStream_t st = as_stream(stream);
+#define CGL_CASE(S)                                                                               \
+    case S:                                                                                       \
+        return launch_env_fused<S>(win, wout, stable, n_envs, actions, spawn, stable_max, reward, \
+                                   alive, err, st, epoch_flags, want, publish)
+    switch (side) {
+        CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
+        CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
+    }
+#undef CGL_CASE
+    return CGL_E_BADARG;
 }
 
 extern "C" int cgl_life_step_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,

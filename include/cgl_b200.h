@@ -85,6 +85,21 @@ int cgl_env_step(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable
                  int stable_max, int32_t *reward_out_dev, uint32_t *alive_out_dev,
                  int *err_flag_dev, cgl_stream_t stream);
 
+/* Chained env steps (fused sides only): identical results to cgl_env_step, but consecutive calls on
+ * the same stream depend on each other PER ENVIRONMENT instead of per launch.  token_dev: uint32
+ * [n_envs].  Env e waits until token[e] == want and stores token[e] = publish when its planes are
+ * written; the caller uses one id per world plane (want = id of world_in, publish = id of
+ * world_out, all tokens initialised to the id of the current plane), which also makes a captured
+ * CUDA graph of an even number of steps replayable.  The next launch's first CTAs then run while this
+ * launch's last CTAs finish (programmatic dependent launch without the grid-wide wait).  Anything
+ * else that touches the state between two chained steps is ordered by the stream as usual.  A
+ * token that does not arrive within ~1 s sets bit 1 of *err_flag_dev instead of hanging. */
+int cgl_env_step_chained(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev,
+                         uint64_t n_envs, uint32_t side, const int32_t *actions_dev, int spawn,
+                         int stable_max, int32_t *reward_out_dev, uint32_t *alive_out_dev,
+                         int *err_flag_dev, uint32_t *token_dev, uint32_t want, uint32_t publish,
+                         cgl_stream_t stream);
+
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
 
