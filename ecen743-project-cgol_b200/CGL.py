@@ -384,7 +384,7 @@ class sim:
                                  stableStabilityFactor=stableStabilityFactor, device=self._dev, states=cells[None, :])
             self._alloc_mirrors()
         else:
-            self._b.spawn, self._b.stable_max = spawnStabilityFactor, stableStabilityFactor
+            self._b.set_factors(spawnStabilityFactor, stableStabilityFactor)
             self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
         self._b.stable.copy_(self._torch.from_numpy(stab)[None, :])
         self._changed()

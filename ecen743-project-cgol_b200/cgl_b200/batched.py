@@ -71,12 +71,14 @@ class BatchedSim:
             self._tokens = torch.zeros(B, dtype=torch.int32, device=self.device) if self.fused else None
             self._plane_id = {self._wa.data_ptr(): 1, self._wb.data_ptr(): 2}
             self._token_plane = None
+            self._step_args = {}
             # Chaining pays when a launch is only a few waves of CTAs deep (its tail is a large share of
-            # it): measured on B200, +9 % at 4096 CTAs (C2), -7 % at 16384 CTAs (the token check adds a
-            # dependent load to every CTA).  CGL_ENV_CHAINED=0/1 forces it off/on.
+            # it): measured on B200 +9 % at 4096 CTAs (C2), +30 % at 2048 CTAs, +46 % at 1024 CTAs (graph
+            # replay), -2 % at 12288 and -3 % at 16384 CTAs (the token check adds a dependent load to every
+            # CTA).  CGL_ENV_CHAINED=0/1 forces it off/on.
             n_ctas = -(-B // max(1, 128 // max(32, side if side > 64 else 32)))
             force = os.environ.get("CGL_ENV_CHAINED")
-            self.chained = self.fused and (force == "1" or (force != "0" and 2400 < n_ctas <= 8192))
+            self.chained = self.fused and (force == "1" or (force != "0" and n_ctas <= 8192))
             self._done = {False: torch.zeros(B, dtype=torch.bool, device=self.device),
                           True: torch.ones(B, dtype=torch.bool, device=self.device)}
             if states is not None:
@@ -149,29 +151,38 @@ class BatchedSim:
         if actions is not None:
             if actions.dtype != torch.int32 or not actions.is_cuda or actions.numel() != self.n_envs:
                 raise TypeError("actions must be an int32 CUDA tensor with one entry per env")
-            actions = actions.contiguous()
-        with torch.cuda.device(self.device):
-            if self.chained:        # per-env dependency between consecutive launches (see the C header)
-                src, dst = self._wa.data_ptr(), self._wb.data_ptr()
-                if self._token_plane != src:        # first chained step, or a non-chained op swapped the planes
-                    self._tokens.fill_(self._plane_id[src])
-                rc = self._lib.cgl_env_step_chained(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                                    self.n_envs, self.side, native.dptr(actions), self.spawn,
-                                                    self.stable_max, native.dptr(self._reward),
-                                                    native.dptr(self._alive) if want_alive else None,
-                                                    native.dptr(self._err), native.dptr(self._tokens),
-                                                    self._plane_id[src], self._plane_id[dst], self._stream())
-                self._token_plane = dst
-            else:
-                rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                            self.n_envs, self.side, native.dptr(actions), self.spawn,
-                                            self.stable_max, native.dptr(self._reward),
-                                            native.dptr(self._alive) if want_alive else None,
-                                            native.dptr(self._err), self._stream())
-        native.check(rc, "cgl_env_step")
+            if not actions.is_contiguous():
+                actions = actions.contiguous()
+        src = self._wa.data_ptr()
+        a_ptr = 0 if actions is None else actions.data_ptr()
+        key = (src, a_ptr, want_alive)
+        args = self._step_args.get(key)
+        if args is None:                                    # ctypes argument tuples are built once per buffer set
+            V = ctypes.c_void_p
+            dst = self._wb.data_ptr()
+            args = [V(src), V(dst), V(self.stable.data_ptr()), self.n_envs, self.side, V(a_ptr), self.spawn,
+                    self.stable_max, V(self._reward.data_ptr()), V(self._alive.data_ptr()) if want_alive else None,
+                    V(self._err.data_ptr())]
+            if self.chained:
+                args += [V(self._tokens.data_ptr()), self._plane_id[src], self._plane_id[dst]]
+            args = (tuple(args), dst, self._lib.cgl_env_step_launches(self.side, int(actions is not None)))
+            if len(self._step_args) > 64:
+                self._step_args.clear()
+            self._step_args[key] = args
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
+        if self.chained:            # per-env dependency between consecutive launches (see the C header)
+            if self._token_plane != src:            # first chained step, or a non-chained op swapped the planes
+                self._tokens.fill_(self._plane_id[src])
+            rc = self._lib.cgl_env_step_chained(*args[0], self._stream())
+            self._token_plane = args[1]
+        else:
+            rc = self._lib.cgl_env_step(*args[0], self._stream())
+        if rc:
+            native.check(rc, "cgl_env_step")
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
-        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions is not None))
+        self.launches += args[2]
         done = self._done[self.max_steps is not None and self.count >= self.max_steps]
         return self.stable, self._reward, done
 
@@ -188,6 +199,13 @@ class BatchedSim:
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
         self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_ptr != 0))
+
+    def set_factors(self, spawnStabilityFactor: int, stableStabilityFactor: int) -> None:
+        """Change the stability constants (sim.load, CGL/CGL.py:348-349); cached launch arguments are dropped."""
+        self.spawn, self.stable_max = spawnStabilityFactor, stableStabilityFactor
+        self._step_args.clear()
+        if hasattr(self, "_host_args"):
+            self._host_args.clear()
 
     def check_actions(self) -> None:
         """Synchronise and raise ValueError if any action since the last check was outside
