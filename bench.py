@@ -372,7 +372,7 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
     torch.cuda.empty_cache()
     # C4: 65536^2 torus, row bands over the ranks, k = 8 generations per launch / per halo exchange
     from cgl_b200.bands import RowBandLife
-    n, k, gens = 65536, (8 if world == 1 else 16), 208      # ghost depth 16 between exchanges, 8 generations per launch
+    n, k, gens = 65536, (8 if world == 1 else 32), 224      # ghost depth 32 between exchanges, 8 generations per launch
     band = RowBandLife(n, n, k=k, rank=rank, world_size=world, device=dev, kernel_k=8)
     band.randomize(1)
     band.run(2 * k)

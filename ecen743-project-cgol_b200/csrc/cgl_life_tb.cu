@@ -46,6 +46,13 @@ struct HaloCtx {
     uint32_t wait_up_target, wait_dn_target;
 };
 
+// Chained launches of one cgl_life_run: strip (cg, rb) of launch j needs the outputs of -- and must
+// not overwrite the inputs of -- the 3 x 3 neighbouring strips of launch j-1.  Each strip publishes
+// tokens[rb * n_cgroups + cg] = j + 1 when it is done and launch j waits for the nine neighbours to
+// reach j; with programmatic dependent launch the first strips of launch j+1 then run while the
+// last strips of launch j finish, which removes the cost of a partly filled last wave.
+struct ChainCtx { uint32_t *tokens; uint32_t want; uint32_t cap; };
+
 // Spin until *ctr - target >= 0 (acquire, system scope); lane 0 polls, the warp follows.
 __device__ __forceinline__ void wait_counter(const uint32_t *ctr, uint32_t target)
 {
@@ -79,7 +86,8 @@ constexpr int TB_THREADS = 128;
 template <int K, bool HALO>
 __global__ void __launch_bounds__(TB_THREADS)
 life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t rows, uint32_t W,
-               uint32_t rpt, int wrap_rows, uint32_t n_cgroups, uint32_t n_rblocks, const HaloCtx hc)
+               uint32_t rpt, int wrap_rows, uint32_t n_cgroups, uint32_t n_rblocks, const HaloCtx hc,
+               const ChainCtx chain)
 {
     // Warps are numbered along the row first (column group fastest).  No early exit: padding warps
     // redo the last strip with stores off, the loop trip count is the same for every warp, and the
@@ -91,6 +99,26 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
     uint32_t rb = warp / n_cgroups;
     const bool warp_ok = rb < n_rblocks;
     rb = warp_ok ? rb : n_rblocks - 1;
+
+    if (!HALO && chain.tokens != nullptr) {                    // kernel-uniform branch
+        cudaTriggerProgrammaticLaunchCompletion();
+        // lanes 0..8 watch one neighbour strip each (columns always wrap, rows wrap on the torus)
+        const int dj = (int)(lane % 3) - 1, di = (int)(lane / 3) - 1;
+        const uint32_t ncg = (cg + n_cgroups + (uint32_t)dj) % n_cgroups;
+        int nrb = (int)rb + di;
+        bool need = lane < 9;
+        if (nrb < 0 || nrb >= (int)n_rblocks) {
+            if (wrap_rows) nrb = nrb < 0 ? nrb + (int)n_rblocks : nrb - (int)n_rblocks;
+            else need = false;
+        }
+        const uint32_t *tp = chain.tokens + (need ? (uint32_t)nrb * n_cgroups + ncg : 0u);
+        uint32_t v, spins = 0;
+        bool ok;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tp) : "memory");
+            ok = !need || (int32_t)(v - chain.want) >= 0;
+        } while (!__all_sync(0xffffffffu, ok) && ++spins < (1u << 22));      // warp-uniform exit, bounded
+    }
 
     const int wi = (int)(cg * TB_COLS + lane) - 1;             // word column of this lane (may be -1 or >= W)
     const uint32_t wcol = wi < 0 ? (uint32_t)(wi + (int)W) : ((uint32_t)wi >= W ? (uint32_t)wi - W : (uint32_t)wi);
@@ -172,6 +200,13 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
             }
         }
     }
+    if (!HALO && chain.tokens != nullptr) {
+        __threadfence();                             // this strip's rows are visible device-wide ...
+        __syncwarp();
+        if (lane == 0 && warp_ok)                    // ... before its token is published
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain.tokens + rb * n_cgroups + cg),
+                         "r"(chain.want + 1) : "memory");
+    }
     if (HALO) {
         __threadfence_system();                      // my peer stores are visible system-wide ...
         __syncwarp();
@@ -229,7 +264,8 @@ static uint32_t strips_touching(uint32_t lo, uint32_t hi, uint32_t rpt, uint32_t
 // (1-based count of band blocks since the ghosts were last filled by a plain exchange).
 template <int K, bool HALO>
 static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t cols, int wrap_rows,
-                     cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0)
+                     cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0, ChainCtx chain = ChainCtx(),
+                     uint32_t *n_strips_out = nullptr)
 {
     static int rpt_knob = -1, occ = 0;   // CGL_TB_ROWS overrides the strip length (tuning)
     if (rpt_knob < 0) {
@@ -256,17 +292,30 @@ static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t 
         halo.wait_up_target = (block_index - 1) * bot;
         halo.wait_dn_target = (block_index - 1) * top;
     }
-    life_tb_kernel<K, HALO><<<(unsigned)blocks, TB_THREADS, 0, st>>>(in, out, rows, W, rpt, wrap_rows, n_cgroups,
-                                                                   n_rblocks, halo);
-    CGL_LAUNCH_CHECK();
+    if (n_strips_out) *n_strips_out = n_cgroups * n_rblocks;
+    // chaining needs the nine-neighbour footprint (strips at least K rows long) and a large enough token buffer
+    if (chain.tokens != nullptr && (rpt < (uint32_t)K || (uint64_t)n_cgroups * n_rblocks > chain.cap)) chain.tokens = nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(TB_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (chain.tokens != nullptr && chain.want > 0) ? 1 : 0;        // the first launch of a run waits normally
+    CGL_CUDA(cudaLaunchKernelEx(&cfg, life_tb_kernel<K, HALO>, in, out, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks,
+                                halo, chain));
     return 0;
 }
 
 template <bool HALO>
 static int tb_dispatch(int k, const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t cols, int wrap_rows,
-                       cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0)
+                       cudaStream_t st, HaloCtx halo = HaloCtx(), uint32_t block_index = 0, ChainCtx chain = ChainCtx(),
+                       uint32_t *n_strips_out = nullptr)
 {
-#define CGL_TB_CASE(KK) case KK: return launch_tb<KK, HALO>(in, out, rows, cols, wrap_rows, st, halo, block_index)
+#define CGL_TB_CASE(KK) \
+    case KK: return launch_tb<KK, HALO>(in, out, rows, cols, wrap_rows, st, halo, block_index, chain, n_strips_out)
     switch (k) {
         CGL_TB_CASE(1); CGL_TB_CASE(2); CGL_TB_CASE(3); CGL_TB_CASE(4);
         CGL_TB_CASE(6); CGL_TB_CASE(8); CGL_TB_CASE(12); CGL_TB_CASE(16);
@@ -274,6 +323,39 @@ static int tb_dispatch(int k, const uint32_t *in, uint32_t *out, uint32_t rows, 
 #undef CGL_TB_CASE
     set_error("cgl_life_run: no temporal-blocking kernel for k=%d", k);
     return CGL_E_BADARG;
+}
+
+// Token buffers of the chained launches, one per (device, stream) so that concurrent streams do not
+// share tokens.  Returns nullptr when chaining is off (CGL_TB_CHAIN=0) or no buffer can be had.
+static uint32_t *chain_tokens(cudaStream_t st, uint32_t rows, uint32_t cols, uint32_t *cap_out)
+{
+    struct TokenBuf { int dev; cudaStream_t st; uint32_t *p; uint32_t cap; };
+    static TokenBuf bufs[16] = {};
+    static int n_bufs = 0, chain_on = -1;
+    if (chain_on < 0) {
+        const char *e = getenv("CGL_TB_CHAIN");
+        chain_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    int dev = 0;
+    if (!chain_on || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    const uint32_t max_strips = ((cols / 32 + TB_COLS - 1) / TB_COLS) * ((rows + 95) / 96 + 1);
+    TokenBuf *tb = nullptr;
+    for (int i = 0; i < n_bufs; ++i)
+        if (bufs[i].dev == dev && bufs[i].st == st) tb = &bufs[i];
+    if (tb == nullptr && n_bufs < 16) {
+        tb = &bufs[n_bufs++];
+        *tb = TokenBuf{dev, st, nullptr, 0};
+    }
+    if (tb == nullptr) return nullptr;
+    if (tb->cap < max_strips) {
+        if (tb->p) cudaFree(tb->p);
+        tb->p = nullptr;
+        tb->cap = 0;
+        if (cudaMalloc(&tb->p, (size_t)max_strips * 4) == cudaSuccess) tb->cap = max_strips;
+        else cudaGetLastError();
+    }
+    *cap_out = tb->cap;
+    return tb->p;
 }
 
 }  // namespace cgl
@@ -298,6 +380,11 @@ extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uin
     uint32_t *src = buf_a, *dst = buf_b;
     uint32_t left = gens;
     const bool tiled = cols % 32 == 0 && cols >= 32 * TB_COLS && rows >= 8;
+    uint32_t token_cap = 0;
+    uint32_t *token_buf = (tiled && k > 1) ? chain_tokens(st, rows, cols, &token_cap) : nullptr;
+    const bool chain_ok = token_buf != nullptr;
+    int prev_step = 0;
+    uint32_t chained = 0;                 // launches of the current chain so far
     while (left > 0) {
         int step = 1;
         if (tiled && k > 1) {
@@ -305,8 +392,22 @@ extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uin
                 if ((uint32_t)s <= k && (uint32_t)s <= left) { step = s; break; }
         }
         int rc;
-        if (step == 1) rc = cgl_life_step(src, dst, 1, rows, cols, wrap_rows, nullptr, stream);
-        else rc = tb_dispatch<false>(step, src, dst, rows, cols, wrap_rows, st);
+        if (step == 1) {
+            rc = cgl_life_step(src, dst, 1, rows, cols, wrap_rows, nullptr, stream);
+            prev_step = 0;
+        } else {
+            ChainCtx chain{nullptr, 0, 0};
+            if (chain_ok) {
+                if (step != prev_step) {   // new geometry: start a new chain behind everything queued so far
+                    CGL_CUDA(cudaMemsetAsync(token_buf, 0, (size_t)token_cap * 4, st));
+                    chained = 0;
+                }
+                chain = ChainCtx{token_buf, chained, token_cap};
+            }
+            rc = tb_dispatch<false>(step, src, dst, rows, cols, wrap_rows, st, HaloCtx(), 0, chain);
+            prev_step = step;
+            ++chained;
+        }
         if (rc) return rc;
         uint32_t *t = src; src = dst; dst = t;
         left -= (uint32_t)step;
@@ -338,14 +439,21 @@ extern "C" int cgl_life_tune(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, ui
     TunedRows &slot = g_tuned[g_n_tuned];
     slot = TunedRows{rows, W, kk, 0};
     ++g_n_tuned;                                   // visible to launch_tb through tuned_rows()
+    uint32_t token_cap = 0;
+    uint32_t *token_buf = chain_tokens(st, rows, cols, &token_cap);
     for (uint32_t rpt : cand) {
         if (rpt < 8u * kk || rpt > rows) continue;
         slot.rpt = rpt;
-        int rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st);      // warm-up
+        // time 4 launches chained like cgl_life_run chains them (all a -> b: every launch writes the same
+        // values, so re-running a strip early is harmless); the first one doubles as warm-up
+        if (token_buf) CGL_CUDA(cudaMemsetAsync(token_buf, 0, (size_t)token_cap * 4, st));
+        int rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st, HaloCtx(), 0, ChainCtx{token_buf, 0, token_cap});
         if (rc) return rc;
         CGL_CUDA(cudaEventRecord(e0, st));
-        for (int rep = 0; rep < 2; ++rep)
-            if ((rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st))) return rc;
+        for (uint32_t rep = 1; rep <= 4; ++rep)
+            if ((rc = tb_dispatch<false>(kk, buf_a, buf_b, rows, cols, wrap_rows, st, HaloCtx(), 0,
+                                         ChainCtx{token_buf, rep, token_cap})))
+                return rc;
         CGL_CUDA(cudaEventRecord(e1, st));
         CGL_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
