@@ -135,7 +135,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         }
         if (t == 0 && active) {
             uint32_t spins = 0;
-            while (v != want && ++spins < (1u << 22))
+            while (v != want && ++spins < (1u << 17))
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
             if (v != want && err_flag != nullptr) atomicOr(err_flag, 2);
         }

@@ -117,7 +117,7 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tp) : "memory");
             ok = !need || (int32_t)(v - chain.want) >= 0;
-        } while (!__all_sync(0xffffffffu, ok) && ++spins < (1u << 22));      // warp-uniform exit, bounded
+        } while (!__all_sync(0xffffffffu, ok) && ++spins < (1u << 17));      // warp-uniform exit, bounded
     }
 
     const int wi = (int)(cg * TB_COLS + lane) - 1;             // word column of this lane (may be -1 or >= W)
