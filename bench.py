@@ -440,7 +440,50 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
         out["c5_life_32768_k_sweep"] = sweep
         del a, b
         torch.cuda.empty_cache()
+        # f1: config 2 under the batched DQN loop (the reference's main.py:58-75 for 4096 envs at once):
+        # select_action -> toggle+step+reward into the replay ring -> learn -> target update, all on the device.
+        # Network = dqn.py:41-59 at side 128 (16384 -> 32770 -> 32770 -> 16385, 2.15 G parameters, fp32).
+        try:
+            out["f1_dqn_loop_4096x128"] = dqn_loop_extra(torch, dev, barrier)
+        except torch.OutOfMemoryError as exc:                    # another tenant on the GPU: report, do not fail the bench
+            out["f1_dqn_loop_4096x128"] = {"skipped": f"out of memory: {str(exc)[:80]}"}
+        torch.cuda.empty_cache()
     return out
+
+
+def dqn_loop_extra(torch, dev, barrier, n_envs=4096, side=128, steps=3):
+    from cgl_b200.batched import BatchedSim
+    from cgl_b200.dqn import BatchedDQNAgent
+    env = BatchedSim(n_envs, side, seed=0, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE, rng="device")
+    agent = BatchedDQNAgent(env, max_size=int(1e5), batch_size=64, seed=0)
+    res = {"n_envs": n_envs, "side": side, "parameters": sum(p.numel() for p in agent.Q.parameters()),
+           "replay_slots": agent.memory.slots, "replay_bytes_moved_per_step": 0}
+    state = [agent.reset()]
+
+    def loop(_i):
+        action = agent.select_action(state[0], 0.1, out=agent.memory.action_slot())
+        state[0], _ = agent.step(action)
+
+    def env_only(_i):
+        agent.memory.step(agent.memory.action_slot())
+
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        loop(0); loop(0)
+        dt = time_steps(torch, loop, steps, barrier) / steps
+        res[name] = {"env_steps_per_s": n_envs / dt, "ms_per_batched_step": dt * 1e3}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    agent.act_dtype = torch.bfloat16                     # opt-in: acting forward on the bf16 tensor cores
+    loop(0); loop(0)
+    dt = time_steps(torch, loop, steps, barrier) / steps
+    res["bf16_acting"] = {"env_steps_per_s": n_envs / dt, "ms_per_batched_step": dt * 1e3}
+    agent.act_dtype = None
+    env_only(0)
+    dt_env = time_steps(torch, env_only, 200, barrier) / 200
+    res["env_step_into_ring_us"] = dt_env * 1e6
+    res["env_share_of_loop_fp32"] = dt_env / (res["fp32"]["ms_per_batched_step"] / 1e3)
+    env.check_actions()
+    return res
 
 
 if __name__ == "__main__":

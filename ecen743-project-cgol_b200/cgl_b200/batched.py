@@ -142,31 +142,67 @@ class BatchedSim:
         self.stable.copy_(self._init_stable)
         return self.stable
 
-    def step(self, actions: torch.Tensor | None = None, want_alive: bool = False):
+    def bind_observation(self, buf: torch.Tensor) -> None:
+        """Move the live stability plane into `buf` (int8 [B, size] on the device): the replay ring of
+        cgl_b200.dqn owns the observation memory and the env steps from slot to slot."""
+        if buf.dtype != torch.int8 or buf.device != self.device or not buf.is_contiguous() \
+                or buf.numel() != self.n_envs * self.size:
+            raise TypeError("buf must be a contiguous int8 tensor [n_envs, size] on the env's device")
+        if buf.data_ptr() != self.stable.data_ptr():
+            buf.view(self.n_envs, self.size).copy_(self.stable)
+            self.stable = buf.view(self.n_envs, self.size)
+
+    def step(self, actions: torch.Tensor | None = None, want_alive: bool = False,
+             obs_out: torch.Tensor | None = None, reward_out: torch.Tensor | None = None):
         """One env step for every env.  actions: int32 [B] on the device (or None = plain step,
         CGL/bench.py:39-40); action == side*side is the reference's "do nothing".
         Returns (obs, reward, done): obs = the live int8 [B, size] stability tensor, reward =
         int32 [B] (overwritten by the next step), done = bool [B] (count >= max_steps; the
-        reference has no terminal state, CGL/main.py:63)."""
+        reference has no terminal state, CGL/main.py:63).
+
+        obs_out (int8 [B, size], contiguous, on the device): the new stability plane is written THERE
+        (the previous plane is left untouched on the fused sides) and becomes `self.stable`; reward_out
+        (int32 [B]) receives the rewards instead of the internal buffer.  The replay ring of
+        cgl_b200.dqn passes its next slot, which makes recording a transition free of copies."""
         if actions is not None:
             if actions.dtype != torch.int32 or not actions.is_cuda or actions.numel() != self.n_envs:
                 raise TypeError("actions must be an int32 CUDA tensor with one entry per env")
             if not actions.is_contiguous():
                 actions = actions.contiguous()
+        if obs_out is not None:
+            if (obs_out.dtype != torch.int8 or obs_out.device != self.device or not obs_out.is_contiguous()
+                    or obs_out.numel() != self.n_envs * self.size):
+                raise TypeError("obs_out must be a contiguous int8 tensor [n_envs, size] on the env's device")
+        if reward_out is not None:
+            if (reward_out.dtype != torch.int32 or reward_out.device != self.device
+                    or not reward_out.is_contiguous() or reward_out.numel() != self.n_envs):
+                raise TypeError("reward_out must be a contiguous int32 tensor [n_envs] on the env's device")
         src = self._wa.data_ptr()
         a_ptr = 0 if actions is None else actions.data_ptr()
-        key = (src, a_ptr, want_alive)
+        s_in = self.stable.data_ptr()
+        s_out = s_in if obs_out is None else obs_out.data_ptr()
+        r_ptr = self._reward.data_ptr() if reward_out is None else reward_out.data_ptr()
+        key = (src, a_ptr, want_alive, s_in, s_out, r_ptr)
         args = self._step_args.get(key)
         if args is None:                                    # ctypes argument tuples are built once per buffer set
             V = ctypes.c_void_p
             dst = self._wb.data_ptr()
-            args = [V(src), V(dst), V(self.stable.data_ptr()), self.n_envs, self.side, V(a_ptr), self.spawn,
-                    self.stable_max, V(self._reward.data_ptr()), V(self._alive.data_ptr()) if want_alive else None,
-                    V(self._err.data_ptr())]
+            args = [V(src), V(dst), V(s_in)]
+            if s_out != s_in:
+                args.append(V(s_out))
+            args += [self.n_envs, self.side, V(a_ptr), self.spawn, self.stable_max, V(r_ptr),
+                     V(self._alive.data_ptr()) if want_alive else None, V(self._err.data_ptr())]
             if self.chained:
                 args += [V(self._tokens.data_ptr()), self._plane_id[src], self._plane_id[dst]]
-            args = (tuple(args), dst, self._lib.cgl_env_step_launches(self.side, int(actions is not None)))
-            if len(self._step_args) > 64:
+            elif s_out != s_in:
+                args += [None, 0, 0]
+            fn = (self._lib.cgl_env_step_io if s_out != s_in else
+                  self._lib.cgl_env_step_chained if self.chained else self._lib.cgl_env_step)
+            n_launch = self._lib.cgl_env_step_launches(self.side, int(actions is not None))
+            if s_out != s_in and not self.fused:
+                n_launch += 1                               # the plane copy of the generic path
+            args = (tuple(args), dst, n_launch, fn)
+            if len(self._step_args) > 4096:
                 self._step_args.clear()
             self._step_args[key] = args
         if torch.cuda.current_device() != self.device.index:
@@ -174,17 +210,17 @@ class BatchedSim:
         if self.chained:            # per-env dependency between consecutive launches (see the C header)
             if self._token_plane != src:            # first chained step, or a non-chained op swapped the planes
                 self._tokens.fill_(self._plane_id[src])
-            rc = self._lib.cgl_env_step_chained(*args[0], self._stream())
             self._token_plane = args[1]
-        else:
-            rc = self._lib.cgl_env_step(*args[0], self._stream())
+        rc = args[3](*args[0], self._stream())
         if rc:
             native.check(rc, "cgl_env_step")
         self._wa, self._wb = self._wb, self._wa
+        if obs_out is not None:
+            self.stable = obs_out.view(self.n_envs, self.size)
         self.count += 1
         self.launches += args[2]
         done = self._done[self.max_steps is not None and self.count >= self.max_steps]
-        return self.stable, self._reward, done
+        return self.stable, (self._reward if reward_out is None else reward_out), done
 
     def step_ptrs(self, actions_ptr: int, reward_ptr: int) -> None:
         """step() with raw pointers: `actions_ptr` (0 = no actions) and `reward_ptr` may be device memory
@@ -285,7 +321,7 @@ class BatchedSim:
         step runs, reward int32 [B] (and the int8 observation if obs_host is given) come back D2H;
         returns after the copies completed.  One C-ABI call: cgl_env_step_host."""
         key = (0 if actions_host is None else actions_host.data_ptr(), reward_host.data_ptr(),
-               0 if obs_host is None else obs_host.data_ptr(), self._wa.data_ptr())
+               0 if obs_host is None else obs_host.data_ptr(), self._wa.data_ptr(), self.stable.data_ptr())
         args = self._host_args.get(key) if hasattr(self, "_host_args") else None
         if args is None:                                    # ctypes argument tuples are built once per buffer set
             if not hasattr(self, "_act_dev"):

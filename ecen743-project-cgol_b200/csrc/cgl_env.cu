@@ -85,10 +85,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
     return v;
 }
 
-template <int S>
+// IO = false: the stability plane is updated in place.  IO = true: it is read from `stable` and the
+// new values go to `stable_out` (another buffer of the same shape) -- the replay ring of the batched
+// DQN loop hands the env its next observation slot, so "adding to the replay buffer" costs no copy.
+template <int S, bool IO>
 __global__ void __launch_bounds__(EnvCfg<S>::THREADS)
 env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out,
-                      int8_t *__restrict__ stable, uint32_t n_envs,
+                      int8_t *stable, int8_t *stable_out, uint32_t n_envs,
                       const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
                       int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish)
@@ -234,6 +237,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         const uint32_t tbn = ((tb >> 8) & 0xffu) * 0x01010101u;   // table-base byte under every nibble
         const uint32_t lane_s = (threadIdx.x & 31) * 4, lane_b = lane_s + 128;
         uint4 *spt = sp + t;                          // this thread's chunks: spt[u * TPE] (immediate offsets)
+        uint4 *spo = IO ? reinterpret_cast<uint4 *>(stable_out + (size_t)e * C::SIZE) + t : spt;
         const uint32_t *mixt = mix + t;
         const uint32_t keep = ~act_mask, put = spawn4 & act_mask;
         // the thread that owns the action's chunk patches it once, outside the unrolled chunk loop
@@ -273,7 +277,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                     s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
                     acc = __dp4a((int)s[k], 0x01010101, acc);
                 }
-                spt[(b0 + u) * C::TPE] = make_uint4(s[0], s[1], s[2], s[3]);
+                spo[(b0 + u) * C::TPE] = make_uint4(s[0], s[1], s[2], s[3]);
             }
         }
     }
@@ -313,7 +317,7 @@ template <int S>
 static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             const int32_t *actions, int spawn, int stable_max, int32_t *reward,
                             uint32_t *alive, int *err, cudaStream_t st, uint32_t *epoch = nullptr, uint32_t want = 0,
-                            uint32_t publish = 0)
+                            uint32_t publish = 0, int8_t *stable_out = nullptr)
 {
     using C = EnvCfg<S>;
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
@@ -321,7 +325,9 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     if (pad < 0) {
         const char *v = getenv("CGL_ENV_SMEM_PAD");
         pad = v ? atoi(v) : 0;
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM + pad));
     }
     cudaLaunchConfig_t cfg = {};
@@ -334,8 +340,14 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S>, win, wout, stable, (uint32_t)n_envs, actions,
-                                rep4(spawn), rep4(stable_max), reward, alive, err, epoch, want, publish));
+    if (stable_out != nullptr && stable_out != stable)
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true>, win, wout, stable, stable_out,
+                                    (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
+                                    epoch, want, publish));
+    else
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false>, win, wout, stable, stable,
+                                    (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
+                                    epoch, want, publish));
     return 0;
 }
 
@@ -689,6 +701,34 @@ extern "C" int cgl_env_step_chained(uint32_t *win, uint32_t *wout, int8_t *stabl
     }
 #undef CGL_CASE
     return CGL_E_BADARG;
+}
+
+// Out-of-place form: the new stability plane goes to `stable_out` (see include/cgl_b200.h).
+extern "C" int cgl_env_step_io(uint32_t *win, uint32_t *wout, const int8_t *stable_in, int8_t *stable_out,
+                               uint64_t n_envs, uint32_t side, const int32_t *actions, int spawn, int stable_max,
+                               int32_t *reward, uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want,
+                               uint32_t publish, cgl_stream_t stream)
+{
+    CGL_REQUIRE(win && wout && stable_in && stable_out && n_envs && side && win != wout, CGL_E_BADARG,
+                "cgl_env_step_io: bad argument");
+    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step_io: n_envs too large");
+    cudaStream_t st = as_stream(stream);
+    if (cgl_env_step_is_fused(side)) {
+#define CGL_CASE(S)                                                                                     \
+    case S:                                                                                             \
+        return launch_env_fused<S>(win, wout, const_cast<int8_t *>(stable_in), n_envs, actions, spawn,  \
+                                   stable_max, reward, alive, err, st, epoch_flags, want, publish, stable_out)
+        switch (side) {
+            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
+            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
+        }
+#undef CGL_CASE
+    }
+    CGL_REQUIRE(epoch_flags == nullptr, CGL_E_BADARG, "cgl_env_step_io: tokens need a fused side");
+    // generic sides: copy the plane, then the in-place three-kernel path on the copy
+    if (stable_in != stable_out)
+        CGL_CUDA(cudaMemcpyAsync(stable_out, stable_in, n_envs * side * side, cudaMemcpyDeviceToDevice, st));
+    return cgl_env_step(win, wout, stable_out, n_envs, side, actions, spawn, stable_max, reward, alive, err, stream);
 }
 
 extern "C" int cgl_life_step_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,

@@ -100,6 +100,19 @@ int cgl_env_step_chained(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t
                          int *err_flag_dev, uint32_t *token_dev, uint32_t want, uint32_t publish,
                          cgl_stream_t stream);
 
+/* Out-of-place env step: as cgl_env_step / cgl_env_step_chained (token_dev == NULL: plain stream order;
+ * otherwise the chained form), but the stability plane is READ from stable_in_dev and the new plane is
+ * WRITTEN to stable_out_dev, a second int8 [n_envs, side*side] buffer (stable_in_dev is left untouched on
+ * the fused sides).  This is how the batched DQN loop records transitions: the caller hands the env the
+ * next slot of its replay ring, so ExperienceReplay.add (CGL/dqn.py:24-36, two state copies per step)
+ * costs no memory traffic.  stable_in_dev == stable_out_dev is the in-place step.  Generic sides copy the
+ * plane first and do not take tokens. */
+int cgl_env_step_io(uint32_t *world_in_dev, uint32_t *world_out_dev, const int8_t *stable_in_dev,
+                    int8_t *stable_out_dev, uint64_t n_envs, uint32_t side, const int32_t *actions_dev,
+                    int spawn, int stable_max, int32_t *reward_out_dev, uint32_t *alive_out_dev,
+                    int *err_flag_dev, uint32_t *token_dev, uint32_t want, uint32_t publish,
+                    cgl_stream_t stream);
+
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
 
