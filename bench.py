@@ -440,6 +440,18 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
         out["c5_life_32768_k_sweep"] = sweep
         del a, b
         torch.cuda.empty_cache()
+        # f3: the reference's own bench loop (CGL/bench.py:39-40: plain steps, no actions) as ONE launch per k
+        # steps with the environments resident in shared memory (cgl_env_run), config 2 shape
+        from cgl_b200.batched import BatchedSim
+        env = BatchedSim(4096, 128, seed=0, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE, rng="device")
+        runk = {}
+        for k in (8, 64):
+            env.run(k)
+            dt = time_steps(torch, lambda _i: env.run(k), 3, barrier) / 3
+            runk[f"k{k}"] = {"gcups": 4096 * 128 * 128 * k / dt / 1e9, "us_per_step": dt / k * 1e6,
+                             "env_steps_per_s": 4096 * k / dt}
+        out["f3_run_in_smem_4096x128"] = runk
+        del env
         # f1: config 2 under the batched DQN loop (the reference's main.py:58-75 for 4096 envs at once):
         # select_action -> toggle+step+reward into the replay ring -> learn -> target update, all on the device.
         # Network = dqn.py:41-59 at side 128 (16384 -> 32770 -> 32770 -> 16385, 2.15 G parameters, fp32).

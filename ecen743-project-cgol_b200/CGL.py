@@ -244,6 +244,35 @@ class sim:
         self._reward_valid = True
         self._changed()
 
+    # ---- extensions (not in CGL/CGL.py): the reference's own loops around step(), run on the device ----
+    def run(self, iters, until_fixed=False):
+        """`iters` plain steps in one launch (the loop of CGL/bench.py:39-40); with until_fixed stop after
+        the first step that leaves the world unchanged (CGL_action+/validate.py:133-139).  Returns the
+        number of steps executed; `count` advances by it."""
+        self._flush()
+        with self._torch.cuda.device(self._dev):
+            _, rew, steps = self._b.run(int(iters), until_fixed=until_fixed)
+            n = int(steps.item())
+            self._m_reward[0] = int(rew.item())
+        self.count += n
+        self._reward_valid = True
+        self._changed()
+        return n
+
+    def breakdown_stable(self):
+        """np.asarray((unique values, counts)) of the stability vector (CGL_action+/CGL.py:294-297)."""
+        self._flush()
+        hist = self._b.breakdown_stable()[0].cpu().numpy()
+        vals = np.nonzero(hist)[0]
+        return np.asarray(((vals - 128).astype(np.int8), hist[vals]))
+
+    def breakdown_state(self):
+        """np.asarray((unique values, counts)) of the world (CGL_action+/CGL.py:300-303)."""
+        self._flush()
+        dead, live = (int(v) for v in self._b.breakdown_state()[0].cpu())
+        vals = [v for v, c in ((0, dead), (1, live)) if c]
+        return np.asarray((np.array(vals, dtype=np.uint8), np.array([c for c in (dead, live) if c])))
+
     def reward(self):
         """np.int32 sum of the stability vector (CGL/CGL.py:255-256)."""
         self._flush()

@@ -222,6 +222,42 @@ class BatchedSim:
         done = self._done[self.max_steps is not None and self.count >= self.max_steps]
         return self.stable, (self._reward if reward_out is None else reward_out), done
 
+    def run(self, max_steps: int, until_fixed: bool = False, want_alive: bool = False):
+        """`max_steps` plain steps (no actions) for every env in ONE launch, the environments resident in
+        shared memory between steps (`cgl_env_run`): the loop of CGL/bench.py:39-40.  With until_fixed
+        an env stops after the first step that leaves its world unchanged -- the convergence loop of
+        CGL_action+/validate.py:133-139 (there: `old = get_state(); step()` then up to LIMIT more
+        compare-and-step rounds, i.e. max_steps = LIMIT + 1) without the per-step host compare.
+        Returns (obs, reward, steps): steps = int32 [B] steps executed per env.  `count` advances by
+        max_steps, the number of steps the batch was asked for."""
+        if not isinstance(max_steps, int) or max_steps < 0:
+            raise ValueError("max_steps must be a non-negative integer")
+        steps = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_env_run(native.dptr(self._wa), native.dptr(self._wa), native.dptr(self.stable),
+                                               self.n_envs, self.side, max_steps, int(until_fixed), self.spawn,
+                                               self.stable_max, native.dptr(steps), native.dptr(self._reward),
+                                               native.dptr(self._alive) if want_alive else None, self._stream()),
+                         "cgl_env_run")
+        self.count += max_steps
+        self.launches += 1
+        return self.stable, self._reward, steps
+
+    def breakdown_stable(self) -> torch.Tensor:
+        """Value counts of every env's stability plane: int64 [B, 256], column v + 128 = number of cells
+        whose stability is v (the device form of breakdown_stable, CGL_action+/CGL.py:294-297)."""
+        hist = torch.empty((self.n_envs, 256), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._lib.cgl_breakdown_stable(native.dptr(self.stable), self.n_envs, self.size,
+                                                        native.dptr(hist), self._stream()), "cgl_breakdown_stable")
+        self.launches += 1
+        return hist.to(torch.int64) & 0xFFFFFFFF
+
+    def breakdown_state(self) -> torch.Tensor:
+        """int64 [B, 2]: dead and live cells per env (breakdown_state, CGL_action+/CGL.py:300-303)."""
+        alive = self.alive()
+        return torch.stack([self.size - alive, alive], dim=1)
+
     def step_ptrs(self, actions_ptr: int, reward_ptr: int) -> None:
         """step() with raw pointers: `actions_ptr` (0 = no actions) and `reward_ptr` may be device memory
         or device-mapped pinned host memory -- the single-env facade passes pinned words so that a step is

@@ -113,6 +113,26 @@ int cgl_env_step_io(uint32_t *world_in_dev, uint32_t *world_out_dev, const int8_
                     int *err_flag_dev, uint32_t *token_dev, uint32_t want, uint32_t publish,
                     cgl_stream_t stream);
 
+/* Many plain env steps (no actions) in ONE launch with each environment resident in shared memory:
+ * the step loop of CGL/bench.py:39-40, and -- with stop_when_fixed -- the convergence loop of
+ * CGL/CGL_action+/validate.py:133-139 (step until a step leaves the world unchanged, at most max_steps
+ * steps; the reference copies the world to the host and compares there after every step).
+ *   world_in_dev / world_out_dev  packed world before / after; MAY alias (each env is read completely
+ *                                 before it is written).   stable_dev is updated in place.
+ *   steps_out_dev  int32 [n_envs] or NULL: steps actually executed per env (== max_steps unless
+ *                  stop_when_fixed ended the env early; the step that found the fixed point counts).
+ *   reward_out_dev / alive_out_dev as in cgl_env_step (of the final state; valid for max_steps == 0 too).
+ * Sides: the fused sides (multiples of 32 up to 256) and any side <= 273. */
+int cgl_env_run(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev, uint64_t n_envs,
+                uint32_t side, uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max,
+                int32_t *steps_out_dev, int32_t *reward_out_dev, uint32_t *alive_out_dev, cgl_stream_t stream);
+
+/* Value counts of the stability plane, the device form of breakdown_stable (CGL/CGL_action+/CGL.py:
+ * 294-297, np.unique(..., return_counts=True)): hist_out_dev uint32 [n_envs][256],
+ * hist[e][v + 128] = number of cells of env e whose stability equals v. */
+int cgl_breakdown_stable(const int8_t *stable_dev, uint64_t n_envs, uint64_t size, uint32_t *hist_out_dev,
+                         cgl_stream_t stream);
+
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
 
