@@ -135,13 +135,23 @@ class sim:
         _say("\tTotal memory:", prop.total_memory / 1048576, "MB")
         _say("\tSMs:", prop.multi_processor_count)
         self._dev = torch.device("cuda", gpu_select)
+        if world0 is None:
+            world0 = self._initial_world()
         self._b = BatchedSim(1, self.side, seed=seed, spawnStabilityFactor=spawnStabilityFactor,
                              stableStabilityFactor=stableStabilityFactor, device=self._dev,
-                             states=None if world0 is None else world0[None, :])
+                             states=None if world0 is None else world0[None, :], **self._env_variant())
         self._alloc_mirrors()
         _say("CGL is now running...")
 
     # ------------------------------------------------------------------------------ internals
+    def _env_variant(self):
+        """Extra BatchedSim keywords; the CGL_action+ facade overrides this (dead-cell rule, masked toggle)."""
+        return {}
+
+    def _initial_world(self):
+        """None = the reference's seeded random start (CGL/CGL.py:104-107); a subclass may return cells."""
+        return None
+
     @staticmethod
     def _validated_cells(flat_u8: np.ndarray) -> np.ndarray:
         if flat_u8.size and flat_u8.max() > 1:
@@ -410,7 +420,8 @@ class sim:
         self.count = count
         if resized:
             self._b = BatchedSim(1, side, seed=self.seed, spawnStabilityFactor=spawnStabilityFactor,
-                                 stableStabilityFactor=stableStabilityFactor, device=self._dev, states=cells[None, :])
+                                 stableStabilityFactor=stableStabilityFactor, device=self._dev, states=cells[None, :],
+                                 **self._env_variant())
             self._alloc_mirrors()
         else:
             self._b.set_factors(spawnStabilityFactor, stableStabilityFactor)

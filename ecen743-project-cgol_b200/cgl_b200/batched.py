@@ -24,6 +24,9 @@ import torch
 from . import native
 
 
+DEAD_RULES = {"zero": 0, "decay": 1, "sat": 2}
+
+
 def reference_initial_world(side: int, seed: int) -> np.ndarray:
     """The reference's random start: CGL/CGL.py:104-107 (legacy MT19937 `np.random.seed`)."""
     return np.random.RandomState(seed).randint(2, size=side * side, dtype=np.uint8)
@@ -32,7 +35,8 @@ def reference_initial_world(side: int, seed: int) -> np.ndarray:
 class BatchedSim:
     def __init__(self, n_envs: int, side: int, seed: int = 0, spawnStabilityFactor: int = -1,
                  stableStabilityFactor: int = 1, device="cuda", states=None, first_env: int = 0,
-                 rng: str = "reference", max_steps: int | None = None):
+                 rng: str = "reference", max_steps: int | None = None, dead_rule: str = "zero", empty: int = 0,
+                 empty_min: int = -128, masked_toggle: bool = False):
         if not isinstance(n_envs, int) or n_envs < 1:
             raise ValueError("n_envs must be a positive integer")
         if not isinstance(side, int) or side < 1:
@@ -42,6 +46,19 @@ class BatchedSim:
                 raise TypeError(f"{name} must be an integer!")
             if not -128 <= v <= 127:
                 raise OverflowError(f"{name}={v} out of bounds for int8")
+        # The CGL_action+ fork's variants (CGL/CGL_action+/CGL.py): what a cell that is dead after the step gets
+        # ("zero" = base env; "decay" = the fork's CUDA kernel :190-193; "sat" = the fork's CPU step :256), the
+        # initial stability of dead cells, and the masked toggle (:382-384).  See cgl_env_step_rule.
+        if dead_rule not in DEAD_RULES:
+            raise ValueError(f"dead_rule must be one of {sorted(DEAD_RULES)}")
+        for name, v in (("empty", empty), ("empty_min", empty_min)):
+            if not isinstance(v, int):
+                raise TypeError(f"{name} must be integer!")
+            if not -128 <= v <= 127:
+                raise OverflowError(f"{name}={v} out of bounds for int8")
+        self.dead_rule, self.empty, self.empty_min = dead_rule, empty, empty_min
+        self.masked_toggle = bool(masked_toggle)
+        self._ext = DEAD_RULES[dead_rule] != 0 or self.masked_toggle
         self._lib = native.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -128,11 +145,11 @@ class BatchedSim:
         self.launches += 1
 
     def init_stable(self) -> None:
-        """stable = alive ? spawn : 0 (CGL/CGL.py:111-112)."""
+        """stable = alive ? spawn : 0 (CGL/CGL.py:111-112); zeros become `empty` (CGL_action+/CGL.py:124-126)."""
         with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_init_stable(native.dptr(self._wa), native.dptr(self.stable),
-                                                   self.n_envs, self.side, self.spawn, self._stream()),
-                         "cgl_init_stable")
+            native.check(self._lib.cgl_init_stable_rule(native.dptr(self._wa), native.dptr(self.stable),
+                                                        self.n_envs, self.side, self.spawn, self.empty,
+                                                        self._stream()), "cgl_init_stable_rule")
         self.launches += 1
 
     # ------------------------------------------------------------------ env API
@@ -187,16 +204,19 @@ class BatchedSim:
         if args is None:                                    # ctypes argument tuples are built once per buffer set
             V = ctypes.c_void_p
             dst = self._wb.data_ptr()
+            io = s_out != s_in or self._ext
             args = [V(src), V(dst), V(s_in)]
-            if s_out != s_in:
+            if io:
                 args.append(V(s_out))
-            args += [self.n_envs, self.side, V(a_ptr), self.spawn, self.stable_max, V(r_ptr),
-                     V(self._alive.data_ptr()) if want_alive else None, V(self._err.data_ptr())]
+            args += [self.n_envs, self.side, V(a_ptr), self.spawn, self.stable_max]
+            if self._ext:
+                args += [DEAD_RULES[self.dead_rule], self.empty, self.empty_min, int(self.masked_toggle)]
+            args += [V(r_ptr), V(self._alive.data_ptr()) if want_alive else None, V(self._err.data_ptr())]
             if self.chained:
                 args += [V(self._tokens.data_ptr()), self._plane_id[src], self._plane_id[dst]]
-            elif s_out != s_in:
+            elif io:
                 args += [None, 0, 0]
-            fn = (self._lib.cgl_env_step_io if s_out != s_in else
+            fn = (self._lib.cgl_env_step_rule if self._ext else self._lib.cgl_env_step_io if io else
                   self._lib.cgl_env_step_chained if self.chained else self._lib.cgl_env_step)
             n_launch = self._lib.cgl_env_step_launches(self.side, int(actions is not None))
             if s_out != s_in and not self.fused:
@@ -232,6 +252,8 @@ class BatchedSim:
         max_steps, the number of steps the batch was asked for."""
         if not isinstance(max_steps, int) or max_steps < 0:
             raise ValueError("max_steps must be a non-negative integer")
+        if DEAD_RULES[self.dead_rule] != 0:
+            raise native.CglNativeError("run() implements the base env's rule only (dead_rule='zero')")
         steps = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             native.check(self._lib.cgl_env_run(native.dptr(self._wa), native.dptr(self._wa), native.dptr(self.stable),
@@ -262,19 +284,29 @@ class BatchedSim:
         """step() with raw pointers: `actions_ptr` (0 = no actions) and `reward_ptr` may be device memory
         or device-mapped pinned host memory -- the single-env facade passes pinned words so that a step is
         one launch with no staging copies."""
-        rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                    self.n_envs, self.side, ctypes.c_void_p(actions_ptr), self.spawn,
-                                    self.stable_max, ctypes.c_void_p(reward_ptr), None, native.dptr(self._err),
-                                    self._stream())
+        if self._ext:
+            rc = self._lib.cgl_env_step_rule(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                             native.dptr(self.stable), self.n_envs, self.side,
+                                             ctypes.c_void_p(actions_ptr), self.spawn, self.stable_max,
+                                             DEAD_RULES[self.dead_rule], self.empty, self.empty_min,
+                                             int(self.masked_toggle), ctypes.c_void_p(reward_ptr), None,
+                                             native.dptr(self._err), None, 0, 0, self._stream())
+        else:
+            rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
+                                        self.n_envs, self.side, ctypes.c_void_p(actions_ptr), self.spawn,
+                                        self.stable_max, ctypes.c_void_p(reward_ptr), None, native.dptr(self._err),
+                                        self._stream())
         if rc:
             native.check(rc, "cgl_env_step")
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
         self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_ptr != 0))
 
-    def set_factors(self, spawnStabilityFactor: int, stableStabilityFactor: int) -> None:
+    def set_factors(self, spawnStabilityFactor: int, stableStabilityFactor: int, empty: int | None = None) -> None:
         """Change the stability constants (sim.load, CGL/CGL.py:348-349); cached launch arguments are dropped."""
         self.spawn, self.stable_max = spawnStabilityFactor, stableStabilityFactor
+        if empty is not None:
+            self.empty = empty
         self._step_args.clear()
         if hasattr(self, "_host_args"):
             self._host_args.clear()
@@ -297,10 +329,25 @@ class BatchedSim:
             raise TypeError("idx must be an int32 CUDA tensor")
         idx = idx.reshape(self.n_envs, -1).contiguous()
         with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_toggle(native.dptr(self._wa), native.dptr(self.stable), self.n_envs,
-                                              self.side, native.dptr(idx), idx.shape[1], self.spawn,
-                                              native.dptr(self._err), self._stream()), "cgl_toggle")
+            native.check(self._lib.cgl_toggle_rule(native.dptr(self._wa), native.dptr(self.stable), self.n_envs,
+                                                   self.side, native.dptr(idx), idx.shape[1], self.spawn,
+                                                   int(self.masked_toggle), native.dptr(self._err),
+                                                   self._stream()), "cgl_toggle_rule")
         self.launches += 1
+
+    def block_action(self, centers: torch.Tensor) -> torch.Tensor:
+        """The fork's 2x2 block action (CGL_action+/helper.py:108-132): for every env the four cells
+        {anchor, right, below, below-right} of the block anchored at `centers[e]` with torus wrap-around;
+        centers[e] >= size is the "do nothing" action (four times `size`).  int32 [B] -> int32 [B, 4] for toggle()."""
+        c = centers.to(torch.int64).reshape(self.n_envs)
+        side, size = self.side, self.size
+        x = c % side
+        y = c - x
+        right = (x + 1) % side
+        down = (y + side) % size
+        idx = torch.stack([x + y, right + y, x + down, right + down], dim=1)
+        idx = torch.where((c < size).unsqueeze(1), idx, torch.full_like(idx, size))
+        return idx.to(torch.int32)
 
     def reward(self) -> torch.Tensor:
         """int32 [B] = sum of each env's stability vector (CGL/CGL.py:255-256)."""
@@ -356,6 +403,8 @@ class BatchedSim:
         """The same step driven from HOST buffers: actions int32 [B] (pinned) are copied H2D, the
         step runs, reward int32 [B] (and the int8 observation if obs_host is given) come back D2H;
         returns after the copies completed.  One C-ABI call: cgl_env_step_host."""
+        if self._ext:
+            raise native.CglNativeError("step_host() implements the base env only (dead_rule='zero', unmasked toggle)")
         key = (0 if actions_host is None else actions_host.data_ptr(), reward_host.data_ptr(),
                0 if obs_host is None else obs_host.data_ptr(), self._wa.data_ptr(), self.stable.data_ptr())
         args = self._host_args.get(key) if hasattr(self, "_host_args") else None

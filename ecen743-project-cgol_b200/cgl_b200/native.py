@@ -39,6 +39,9 @@ SIGNATURES = {
     "cgl_env_step_chained": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "cgl_env_run": (_i, [_vp, _vp, _vp, _u64, _u32, _u32, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cgl_breakdown_stable": (_i, [_vp, _u64, _u64, _vp, _vp]),
+    "cgl_env_step_rule": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "cgl_toggle_rule": (_i, [_vp, _vp, _u64, _u32, _vp, _u32, _i, _i, _vp, _vp]),
+    "cgl_init_stable_rule": (_i, [_vp, _vp, _u64, _u32, _i, _i, _vp]),
     "cgl_env_step_io": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "cgl_env_step_is_fused": (_i, [_u32]),
     "cgl_env_step_launches": (_i, [_u32, _i]),

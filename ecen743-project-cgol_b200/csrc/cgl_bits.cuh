@@ -105,6 +105,73 @@ CGL_HD uint32_t stable_update4(uint32_t s, uint32_t surv_mask, uint32_t born_spa
     return (inc_unless_max4(s, max4) & surv_mask) | born_spawn;
 }
 
+// ---- the CGL_action+ fork's rule for cells that are dead after the step ------------------
+// The base env zeroes them (CGL/CGL.py:179,242).  The fork lets them decay; its CUDA kernel and its CPU
+// step disagree, so both are here:
+//   CGL_DEAD_ZERO  (0)  s' = 0
+//   CGL_DEAD_DECAY (1)  s' = (s == EMPTY_MIN) ? s : int8(s - 1)     CGL_action+/CGL.py:190-193 (kernel `run`)
+//   CGL_DEAD_SAT   (2)  s' = min(int8(s + EMPTY), EMPTY_MIN)        CGL_action+/CGL.py:256 (__step_state_cpu)
+enum { CGL_DEAD_ZERO = 0, CGL_DEAD_DECAY = 1, CGL_DEAD_SAT = 2 };
+
+// Per byte: (x != MIN) ? x - 1 : x, int8 wrap-around, no borrow between bytes.
+CGL_HD uint32_t dec_unless_min4(uint32_t s, uint32_t min4)
+{
+    const uint32_t H = 0x80808080u;
+    uint32_t x = s ^ min4;
+    uint32_t ne1 = ((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & H) >> 7;      // 1 where byte != MIN
+    return ((s | H) - ne1) ^ (s & H) ^ H;                                    // bytewise s - ne1
+}
+
+// Per byte int8(a + b) with wrap-around.
+CGL_HD uint32_t add_wrap4(uint32_t a, uint32_t b)
+{
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+
+// Per byte signed minimum.
+CGL_HD uint32_t min_s8x4(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmins4(a, b);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int8_t x = (int8_t)(a >> (8 * i)), y = (int8_t)(b >> (8 * i));
+        r |= (uint32_t)(uint8_t)(x < y ? x : y) << (8 * i);
+    }
+    return r;
+#endif
+}
+
+CGL_HD uint32_t dead_value4(int rule, uint32_t s, uint32_t min4, uint32_t empty4)
+{
+    if (rule == CGL_DEAD_DECAY) return dec_unless_min4(s, min4);
+    if (rule == CGL_DEAD_SAT) return min_s8x4(add_wrap4(s, empty4), min4);
+    return 0u;
+}
+
+// stable' for 4 cells with a dead-cell rule: surv_mask / born_mask are byte masks (0xFF) of the cells that
+// stayed alive / were born.
+CGL_HD uint32_t stable_update4_rule(int rule, uint32_t s, uint32_t surv_mask, uint32_t born_mask, uint32_t spawn4,
+                                    uint32_t max4, uint32_t min4, uint32_t empty4)
+{
+    const uint32_t live = (inc_unless_max4(s, max4) & surv_mask) | (spawn4 & born_mask);
+    return live | (dead_value4(rule, s, min4, empty4) & ~(surv_mask | born_mask));
+}
+
+CGL_HD int8_t stable_update1_rule(int rule, int8_t s, bool prev, bool next, int8_t spawn, int8_t stable_max,
+                                  int8_t empty, int8_t empty_min)
+{
+    if (next && prev) return (s != stable_max) ? (int8_t)(s + 1) : s;
+    if (next) return spawn;
+    if (rule == CGL_DEAD_DECAY) return (s != empty_min) ? (int8_t)(s - 1) : s;
+    if (rule == CGL_DEAD_SAT) {
+        const int8_t t = (int8_t)(s + empty);
+        return t < empty_min ? t : empty_min;
+    }
+    return 0;
+}
+
 // Expand a 4-bit nibble to 4 byte masks (bit i -> byte i = 0xFF).
 CGL_HD uint32_t nibble_to_bytemask(uint32_t nib)
 {

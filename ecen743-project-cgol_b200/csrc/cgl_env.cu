@@ -85,16 +85,23 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
     return v;
 }
 
+struct RuleArgs { int rule, empty, empty_min, masked; };
+
 // IO = false: the stability plane is updated in place.  IO = true: it is read from `stable` and the
 // new values go to `stable_out` (another buffer of the same shape) -- the replay ring of the batched
 // DQN loop hands the env its next observation slot, so "adding to the replay buffer" costs no copy.
-template <int S, bool IO>
+// EXT = true: the CGL_action+ fork's variants (cgl_bits.cuh): `rule` for cells that are dead after the step
+// (decay / saturate instead of zero; min4 / empty4 = EMPTY_MIN / EMPTY replicated) and `masked` toggles
+// (a cell toggled to dead gets 0, not SPAWN: CGL_action+/CGL.py:382-384).  EXT = false is the base env and
+// compiles to exactly the code it had before these parameters existed.
+template <int S, bool IO, bool EXT>
 __global__ void __launch_bounds__(EnvCfg<S>::THREADS)
 env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out,
                       int8_t *stable, int8_t *stable_out, uint32_t n_envs,
                       const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
-                      int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish)
+                      int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish,
+                      int rule, uint32_t min4, uint32_t empty4, int masked)
 {
     using C = EnvCfg<S>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -239,7 +246,12 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         uint4 *spt = sp + t;                          // this thread's chunks: spt[u * TPE] (immediate offsets)
         uint4 *spo = IO ? reinterpret_cast<uint4 *>(stable_out + (size_t)e * C::SIZE) + t : spt;
         const uint32_t *mixt = mix + t;
-        const uint32_t keep = ~act_mask, put = spawn4 & act_mask;
+        uint32_t put = spawn4 & act_mask;
+        if constexpr (EXT) {
+            // masked toggle: the cell's state AFTER the toggle decides (cur holds the toggled plane)
+            if (masked && act >= 0 && !((cur[act_word] >> (act & 31)) & 1u)) put = 0u;
+        }
+        const uint32_t keep = ~act_mask;
         // the thread that owns the action's chunk patches it once, outside the unrolled chunk loop
         auto patch = [&](uint4 &v) {
             if (act_sub == 0) v.x = (v.x & keep) | put;
@@ -273,8 +285,13 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                 for (int k = 0; k < 4; ++k) {
                     // address bytes: [lane*4 (+128 for the born table), TBhi | nibble, 0, 0]
                     const uint32_t surv_mask = lds_u32(__byte_perm(sv, lane_s, 0x5504 + 16 * k));
-                    const uint32_t born_spawn = lds_u32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
-                    s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
+                    if constexpr (EXT) {
+                        const uint32_t born_mask = lds_u32(__byte_perm(bn, lane_s, 0x5504 + 16 * k));
+                        s[k] = stable_update4_rule(rule, s[k], surv_mask, born_mask, spawn4, max4, min4, empty4);
+                    } else {
+                        const uint32_t born_spawn = lds_u32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
+                        s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
+                    }
                     acc = __dp4a((int)s[k], 0x01010101, acc);
                 }
                 spo[(b0 + u) * C::TPE] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -317,7 +334,7 @@ template <int S>
 static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             const int32_t *actions, int spawn, int stable_max, int32_t *reward,
                             uint32_t *alive, int *err, cudaStream_t st, uint32_t *epoch = nullptr, uint32_t want = 0,
-                            uint32_t publish = 0, int8_t *stable_out = nullptr)
+                            uint32_t publish = 0, int8_t *stable_out = nullptr, const RuleArgs *ext = nullptr)
 {
     using C = EnvCfg<S>;
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
@@ -325,10 +342,12 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     if (pad < 0) {
         const char *v = getenv("CGL_ENV_SMEM_PAD");
         pad = v ? atoi(v) : 0;
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      C::SMEM + pad));
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -340,14 +359,19 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (stable_out != nullptr && stable_out != stable)
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true>, win, wout, stable, stable_out,
+    if (ext != nullptr)                 // fork variants: one instantiation (separate in/out planes; they may alias)
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, true>, win, wout, stable,
+                                    stable_out != nullptr ? stable_out : stable, (uint32_t)n_envs, actions,
+                                    rep4(spawn), rep4(stable_max), reward, alive, err, epoch, want, publish,
+                                    ext->rule, rep4(ext->empty_min), rep4(ext->empty), ext->masked));
+    else if (stable_out != nullptr && stable_out != stable)
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, false>, win, wout, stable, stable_out,
                                     (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
-                                    epoch, want, publish));
+                                    epoch, want, publish, 0, 0u, 0u, 0));
     else
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false>, win, wout, stable, stable,
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false, false>, win, wout, stable, stable,
                                     (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
-                                    epoch, want, publish));
+                                    epoch, want, publish, 0, 0u, 0u, 0));
     return 0;
 }
 
@@ -360,7 +384,7 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
 __global__ void toggle_kernel(uint32_t *__restrict__ world, int8_t *__restrict__ stable,
                               uint64_t n_envs, uint32_t side, uint32_t W,
                               const int32_t *__restrict__ idx, uint32_t k, int8_t spawn,
-                              int *__restrict__ err_flag)
+                              int *__restrict__ err_flag, int masked)
 {
     const uint64_t size = (uint64_t)side * side;
     for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_envs;
@@ -377,8 +401,10 @@ __global__ void toggle_kernel(uint32_t *__restrict__ world, int8_t *__restrict__
             for (uint32_t j2 = 0; j2 < j; ++j2) dup |= (my[j2] == my[j]);
             if (dup) continue;
             const uint32_t r = (uint32_t)((uint64_t)a / side), c = (uint32_t)((uint64_t)a % side);
-            world[(e * side + r) * W + (c >> 5)] ^= 1u << (c & 31);
-            stable[e * size + a] = spawn;                    // even when toggled to dead (N2)
+            const uint32_t word = world[(e * side + r) * W + (c >> 5)] ^ (1u << (c & 31));
+            world[(e * side + r) * W + (c >> 5)] = word;
+            // base env: SPAWN even when toggled to dead (N2); fork: SPAWN * new state (CGL_action+/CGL.py:382-384)
+            stable[e * size + a] = (masked && !((word >> (c & 31)) & 1u)) ? (int8_t)0 : spawn;
         }
     }
 }
@@ -421,7 +447,7 @@ __global__ void life_generic_kernel(const uint32_t *__restrict__ in, uint32_t *_
 __global__ void stable_generic_kernel(const uint32_t *__restrict__ prev, const uint32_t *__restrict__ next,
                                       int8_t *__restrict__ stable, uint64_t n_envs, uint32_t side,
                                       uint32_t W, int8_t spawn, int8_t stable_max,
-                                      int32_t *__restrict__ reward_out)
+                                      int32_t *__restrict__ reward_out, int rule, int8_t empty, int8_t empty_min)
 {
     const uint64_t size = (uint64_t)side * side;
     const uint64_t total = n_envs * size;
@@ -433,7 +459,7 @@ __global__ void stable_generic_kernel(const uint32_t *__restrict__ prev, const u
         const uint64_t widx = (e * side + r) * W + (c >> 5);
         const bool p = (prev[widx] >> (c & 31)) & 1u;
         const bool n = (next[widx] >> (c & 31)) & 1u;
-        const int8_t s = stable_update1(stable[i], p, n, spawn, stable_max);
+        const int8_t s = stable_update1_rule(rule, stable[i], p, n, spawn, stable_max, empty, empty_min);
         stable[i] = s;
         if (reward_out != nullptr) {
             const unsigned peers = __match_any_sync(__activemask(), e);
@@ -474,10 +500,11 @@ __global__ void pack_kernel(const uint8_t *__restrict__ cells, uint32_t *__restr
     }
 }
 
-// One thread per cell.  mode 0: cells = bit.  mode 1: stable = bit ? spawn : 0.
+// One thread per cell.  mode 0: cells = bit.  mode 1: stable = bit ? spawn : 0, zeros then replaced by
+// `empty` (CGL/CGL.py:111-112; the fork's `stable[stable == 0] = empty`, CGL_action+/CGL.py:124-126).
 __global__ void unpack_kernel(const uint32_t *__restrict__ world, uint8_t *__restrict__ cells,
                               uint64_t n_envs, uint32_t rows, uint32_t cols, uint32_t W,
-                              int mode, uint8_t spawn)
+                              int mode, uint8_t spawn, uint8_t empty = 0)
 {
     const uint64_t total = n_envs * rows * cols;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
@@ -485,7 +512,8 @@ __global__ void unpack_kernel(const uint32_t *__restrict__ world, uint8_t *__res
         const uint64_t row = i / cols;
         const uint32_t c = (uint32_t)(i - row * cols);
         const uint32_t bit = (world[row * W + (c >> 5)] >> (c & 31)) & 1u;
-        cells[i] = mode == 0 ? (uint8_t)bit : (bit ? spawn : (uint8_t)0);
+        const uint8_t v = bit ? spawn : (uint8_t)0;
+        cells[i] = mode == 0 ? (uint8_t)bit : (v ? v : empty);
     }
 }
 
@@ -606,7 +634,31 @@ extern "C" int cgl_toggle(uint32_t *world, int8_t *stable, uint64_t n_envs, uint
     CGL_REQUIRE(world && stable && n_envs && side && idx, CGL_E_BADARG, "cgl_toggle: bad argument");
     if (k == 0) return 0;
     toggle_kernel<<<grid_for(n_envs, 128), 128, 0, as_stream(stream)>>>(
-        world, stable, n_envs, side, cgl_words_per_row(side), idx, k, (int8_t)spawn, err_flag);
+        world, stable, n_envs, side, cgl_words_per_row(side), idx, k, (int8_t)spawn, err_flag, 0);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_toggle_rule(uint32_t *world, int8_t *stable, uint64_t n_envs, uint32_t side,
+                               const int32_t *idx, uint32_t k, int spawn, int masked, int *err_flag,
+                               cgl_stream_t stream)
+{
+    CGL_REQUIRE(world && stable && n_envs && side && idx, CGL_E_BADARG, "cgl_toggle_rule: bad argument");
+    if (k == 0) return 0;
+    toggle_kernel<<<grid_for(n_envs, 128), 128, 0, as_stream(stream)>>>(
+        world, stable, n_envs, side, cgl_words_per_row(side), idx, k, (int8_t)spawn, err_flag, masked);
+    CGL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cgl_init_stable_rule(const uint32_t *world, int8_t *stable, uint64_t n_envs, uint32_t side,
+                                    int spawn, int empty, cgl_stream_t stream)
+{
+    CGL_REQUIRE(stable && world && n_envs && side, CGL_E_BADARG, "cgl_init_stable_rule: bad argument");
+    const uint64_t total = n_envs * side * side;
+    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
+        (uint8_t)(int8_t)spawn, (uint8_t)(int8_t)empty);
     CGL_LAUNCH_CHECK();
     return 0;
 }
@@ -675,7 +727,7 @@ extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint6
     if (reward != nullptr) CGL_CUDA(cudaMemsetAsync(reward, 0, n_envs * sizeof(int32_t), st));
     const uint64_t total = n_envs * side * side;
     stable_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-        win, wout, stable, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward);
+        win, wout, stable, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward, CGL_DEAD_ZERO, 0, 0);
     CGL_LAUNCH_CHECK();
     return 0;
 }
@@ -729,6 +781,51 @@ extern "C" int cgl_env_step_io(uint32_t *win, uint32_t *wout, const int8_t *stab
     if (stable_in != stable_out)
         CGL_CUDA(cudaMemcpyAsync(stable_out, stable_in, n_envs * side * side, cudaMemcpyDeviceToDevice, st));
     return cgl_env_step(win, wout, stable_out, n_envs, side, actions, spawn, stable_max, reward, alive, err, stream);
+}
+
+// The CGL_action+ fork's env step: see include/cgl_b200.h.
+extern "C" int cgl_env_step_rule(uint32_t *win, uint32_t *wout, const int8_t *stable_in, int8_t *stable_out,
+                                 uint64_t n_envs, uint32_t side, const int32_t *actions, int spawn, int stable_max,
+                                 int dead_rule, int empty, int empty_min, int masked_toggle, int32_t *reward,
+                                 uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want, uint32_t publish,
+                                 cgl_stream_t stream)
+{
+    CGL_REQUIRE(win && wout && stable_in && stable_out && n_envs && side && win != wout, CGL_E_BADARG,
+                "cgl_env_step_rule: bad argument");
+    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step_rule: n_envs too large");
+    CGL_REQUIRE(dead_rule >= CGL_DEAD_ZERO && dead_rule <= CGL_DEAD_SAT, CGL_E_BADARG,
+                "cgl_env_step_rule: dead_rule must be 0 (zero), 1 (decay) or 2 (saturate)");
+    CGL_REQUIRE(empty >= -128 && empty <= 127 && empty_min >= -128 && empty_min <= 127, CGL_E_BADARG,
+                "cgl_env_step_rule: empty / empty_min must fit int8");
+    cudaStream_t st = as_stream(stream);
+    const RuleArgs ext = {dead_rule, empty, empty_min, masked_toggle != 0};
+    if (cgl_env_step_is_fused(side)) {
+#define CGL_CASE(S)                                                                                     \
+    case S:                                                                                             \
+        return launch_env_fused<S>(win, wout, const_cast<int8_t *>(stable_in), n_envs, actions, spawn,  \
+                                   stable_max, reward, alive, err, st, epoch_flags, want, publish, stable_out, &ext)
+        switch (side) {
+            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
+            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
+        }
+#undef CGL_CASE
+    }
+    CGL_REQUIRE(epoch_flags == nullptr, CGL_E_BADARG, "cgl_env_step_rule: tokens need a fused side");
+    if (stable_in != stable_out)
+        CGL_CUDA(cudaMemcpyAsync(stable_out, stable_in, n_envs * side * side, cudaMemcpyDeviceToDevice, st));
+    const uint32_t W = cgl_words_per_row(side);
+    if (actions != nullptr) {
+        int rc = cgl_toggle_rule(win, stable_out, n_envs, side, actions, 1, spawn, masked_toggle, err, stream);
+        if (rc) return rc;
+    }
+    int rc = cgl_life_step(win, wout, n_envs, side, side, 1, alive, stream);
+    if (rc) return rc;
+    if (reward != nullptr) CGL_CUDA(cudaMemsetAsync(reward, 0, n_envs * sizeof(int32_t), st));
+    stable_generic_kernel<<<grid_for(n_envs * side * side, 256), 256, 0, st>>>(
+        win, wout, stable_out, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward, dead_rule,
+        (int8_t)empty, (int8_t)empty_min);
+    CGL_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int cgl_life_step_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,

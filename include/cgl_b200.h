@@ -133,6 +133,34 @@ int cgl_env_run(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *s
 int cgl_breakdown_stable(const int8_t *stable_dev, uint64_t n_envs, uint64_t size, uint32_t *hist_out_dev,
                          cgl_stream_t stream);
 
+/* ---- the CGL_action+ fork of the env (CGL/CGL_action+/CGL.py) --------------------------------
+ * Same step with three differences, each an argument here:
+ *   dead_rule      what a cell that is dead after the step gets:
+ *                    0  0                                            (the base env, CGL/CGL.py:179,242)
+ *                    1  (s == empty_min) ? s : int8(s - 1)           (the fork's CUDA kernel, :190-193)
+ *                    2  min(int8(s + empty), empty_min)              (the fork's CPU step, :256)
+ *                  the fork's two back ends disagree, so the caller chooses which one to reproduce;
+ *   masked_toggle  1: a toggled cell gets SPAWN only if it is alive after the toggle, else 0 (:382-384);
+ *                  0: SPAWN either way (base env, CGL/CGL.py:326);
+ *   empty          initial stability of dead cells (cgl_init_stable_rule; also replaces a 0 SPAWN, :124-126).
+ * Everything else (planes, actions, tokens, stable_in/out, outputs) is as in cgl_env_step_io; with
+ * dead_rule = 0, masked_toggle = 0 the results equal cgl_env_step's. */
+int cgl_env_step_rule(uint32_t *world_in_dev, uint32_t *world_out_dev, const int8_t *stable_in_dev,
+                      int8_t *stable_out_dev, uint64_t n_envs, uint32_t side, const int32_t *actions_dev,
+                      int spawn, int stable_max, int dead_rule, int empty, int empty_min, int masked_toggle,
+                      int32_t *reward_out_dev, uint32_t *alive_out_dev, int *err_flag_dev, uint32_t *token_dev,
+                      uint32_t want, uint32_t publish, cgl_stream_t stream);
+
+/* cgl_toggle with the fork's masked stability write (masked = 1), K indices per env
+ * (CGL_action+/helper.py:108-132 passes the four cells of a 2x2 block). */
+int cgl_toggle_rule(uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_t side,
+                    const int32_t *idx_dev, uint32_t k, int spawn, int masked, int *err_flag_dev,
+                    cgl_stream_t stream);
+
+/* stable = alive ? spawn : 0, then zeros -> empty (CGL_action+/CGL.py:122-126). */
+int cgl_init_stable_rule(const uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_t side,
+                         int spawn, int empty, cgl_stream_t stream);
+
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
 

@@ -61,3 +61,33 @@ TRACES = _load_traces()
 @pytest.fixture(scope="session")
 def traces():
     return TRACES
+
+
+class ForkTrace(Trace):
+    """One recorded run of the CGL_action+ fork's CPU back end (tests/golden/make_golden_action_plus.py)."""
+
+    def __init__(self, z, name):
+        self.name = name
+        self.side = int(z[f"{name}/side"])
+        self.size = self.side * self.side
+        self.spawn = int(z[f"{name}/spawn"])
+        self.stable_max = int(z[f"{name}/stable_max"])
+        self.empty = int(z[f"{name}/empty"])
+        self.empty_min = int(z[f"{name}/empty_min"])
+        self.worlds = np.unpackbits(z[f"{name}/worlds"], axis=1)[:, :self.size]
+        self.stables = z[f"{name}/stables"]
+        self.toggled_stables = z[f"{name}/toggled_stables"]
+        self.stability = z[f"{name}/stability"]
+        self.alives = z[f"{name}/alives"]
+        self.actions = z[f"{name}/actions"]
+        self.max_density = float(z[f"{name}/max_density"])
+        self.T = self.actions.shape[0]
+
+
+def _load_fork_traces():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_action_plus.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    return {n: ForkTrace(z, n) for n in names}
+
+
+FORK_TRACES = _load_fork_traces()

@@ -132,4 +132,48 @@ int twin_env_step_fused(const uint32_t *world_in, uint32_t *world_out, int8_t *s
     return err;
 }
 
+// mirrors stable_generic_kernel with the CGL_action+ dead-cell rules
+void twin_stable_generic_rule(const uint32_t *prev, const uint32_t *next, int8_t *stable, uint64_t n_envs,
+                              uint32_t side, int spawn, int stable_max, int rule, int empty, int empty_min)
+{
+    const uint32_t W = (side + 31) / 32;
+    const uint64_t size = (uint64_t)side * side;
+    for (uint64_t e = 0; e < n_envs; ++e)
+        for (uint32_t r = 0; r < side; ++r)
+            for (uint32_t c = 0; c < side; ++c) {
+                const uint64_t widx = (e * side + r) * W + (c >> 5);
+                const bool p = (prev[widx] >> (c & 31)) & 1u, n = (next[widx] >> (c & 31)) & 1u;
+                int8_t &s = stable[e * size + (uint64_t)r * side + c];
+                s = stable_update1_rule(rule, s, p, n, (int8_t)spawn, (int8_t)stable_max, (int8_t)empty,
+                                        (int8_t)empty_min);
+            }
+}
+
+// Exhaustive check of the 4-cells-per-word rule against the scalar rule: every stability byte in every
+// lane, every transition (survive / born / dead), neighbours in the word holding other values.
+uint64_t twin_rule_mismatches(int rule, int spawn, int stable_max, int empty, int empty_min)
+{
+    uint64_t bad = 0;
+    const uint32_t spawn4 = rep4(spawn), max4 = rep4(stable_max), min4 = rep4(empty_min), empty4 = rep4(empty);
+    for (int lane = 0; lane < 4; ++lane)
+        for (int v = 0; v < 256; ++v)
+            for (int tr = 0; tr < 3; ++tr)
+                for (int other = 0; other < 3; ++other) {
+                    uint32_t s = 0, surv = 0, born = 0;
+                    int8_t want[4];
+                    for (int b = 0; b < 4; ++b) {
+                        const int8_t sv = (int8_t)(b == lane ? v : (v * 7 + 31 * b + 13) & 0xff);
+                        const int t = b == lane ? tr : (other + b) % 3;
+                        s |= (uint32_t)(uint8_t)sv << (8 * b);
+                        if (t == 0) surv |= 0xffu << (8 * b);
+                        if (t == 1) born |= 0xffu << (8 * b);
+                        want[b] = stable_update1_rule(rule, sv, t == 0, t != 2, (int8_t)spawn, (int8_t)stable_max,
+                                                      (int8_t)empty, (int8_t)empty_min);
+                    }
+                    const uint32_t got = stable_update4_rule(rule, s, surv, born, spawn4, max4, min4, empty4);
+                    for (int b = 0; b < 4; ++b) bad += (int8_t)(got >> (8 * b)) != want[b];
+                }
+    return bad;
+}
+
 }  // extern "C"
