@@ -452,6 +452,21 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
                              "env_steps_per_s": 4096 * k / dt}
         out["f3_run_in_smem_4096x128"] = runk
         del env
+        # f2: the CGL_action+ fork's rule (dead cells decay to a floor, masked toggle) in the same fused kernel
+        g = torch.Generator(device=dev)
+        g.manual_seed(11)
+        acts = torch.randint(0, 128 * 128 + 1, (4096,), dtype=torch.int32, device=dev, generator=g)
+        fork_rates = {}
+        for rule in ("decay", "sat"):
+            envs = [BatchedSim(4096, 128, seed=i, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE, rng="device",
+                               dead_rule=rule, empty=-1, empty_min=-6, masked_toggle=True) for i in range(4)]
+            for i in range(8):
+                envs[i % 4].step(acts)
+            dt = time_steps(torch, lambda i: envs[i % 4].step(acts), 400, barrier) / 400
+            fork_rates[rule] = {"gcups": 4096 * 128 * 128 / dt / 1e9, "us_per_step": dt * 1e6,
+                                "hbm_frac": BYTES_PER_CELL_ENV * 4096 * 128 * 128 / dt / 1e9 / peak}
+            del envs
+        out["f2_fork_rule_4096x128"] = fork_rates
         # f1: config 2 under the batched DQN loop (the reference's main.py:58-75 for 4096 envs at once):
         # select_action -> toggle+step+reward into the replay ring -> learn -> target update, all on the device.
         # Network = dqn.py:41-59 at side 128 (16384 -> 32770 -> 32770 -> 16385, 2.15 G parameters, fp32).
