@@ -166,8 +166,18 @@ class BatchedDQNAgent:
 
     def __init__(self, env, discount: float = 0.99, tau: float = 1e-3, lr: float = 5e-4, update_freq: int = 4,
                  max_size: int = int(1e5), batch_size: int = 64, seed: int = 0, hidden: int | None = None,
-                 act_dtype: torch.dtype | None = None):
+                 act_dtype: torch.dtype | None = None, group=None):
         self.env = env
+        # Data parallel over GPUs: every rank owns a shard of the environments
+        # (BatchedSim.shard) and of the replay ring; the only exchange is the gradient all-reduce in learn().
+        # group: a torch.distributed process group, or True for the default group.  All ranks must pass the
+        # same seed (identical initial weights); exploration and sampling streams are offset by the rank.
+        self.group = None
+        self.world_size, self.rank = 1, 0
+        if group is not None and group is not False:
+            import torch.distributed as dist
+            self.group = dist.group.WORLD if group is True else group
+            self.world_size, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         # act_dtype (opt-in, e.g. torch.bfloat16): run the ACTING forward of select_action in that type on the
         # tensor cores (weights are re-cast from the fp32 master copy each call).  The reference acts in fp32
         # (dqn.py:56 and its "can change this to float16" note); near-ties of Q may then pick another action.
@@ -177,7 +187,7 @@ class BatchedDQNAgent:
         self.discount, self.tau, self.lr = float(discount), float(tau), float(lr)
         self.update_freq, self.batch_size = update_freq, batch_size
         self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(seed)
+        self._gen.manual_seed(seed + 7919 * self.rank)
         prev = torch.random.get_rng_state()
         torch.manual_seed(seed)                                           # weight init, reproducible per seed
         self.Q = QNetwork(self.state_dim, self.action_dim, hidden, self.device)
@@ -185,7 +195,7 @@ class BatchedDQNAgent:
         torch.random.set_rng_state(prev)
         # one multi-tensor launch per update on the GPU (same arithmetic as the reference's optim.Adam)
         self.optimizer = torch.optim.Adam(self.Q.parameters(), lr=self.lr, fused=self.device.type == "cuda")
-        self.memory = TrajectoryReplay(env, max_size, batch_size, seed)
+        self.memory = TrajectoryReplay(env, max_size, batch_size, seed + 7919 * self.rank)
         self.t_train = 0
 
     # -- acting -------------------------------------------------------------------------------------
@@ -239,6 +249,13 @@ class BatchedDQNAgent:
         loss = F.mse_loss(q, target_q)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
+        if self.world_size > 1:                      # mean over ranks == the gradient of the loss over the union batch
+            import torch.distributed as dist
+            grads = [p.grad for p in self.Q.parameters()]
+            work = [dist.all_reduce(g, group=self.group, async_op=True) for g in grads]
+            for w in work:
+                w.wait()
+            torch._foreach_div_(grads, float(self.world_size))
         self.optimizer.step()
         self.target_update(self.Q, self.Q_target, self.tau)
         return loss.detach()

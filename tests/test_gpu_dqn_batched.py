@@ -127,3 +127,18 @@ def test_batched_dqn_loop_on_device(cuda):
     assert len(losses) == 24 and all(torch.isfinite(l) for l in losses)
     assert not torch.equal(agent.Q.l1.weight, w0) and not torch.equal(agent.Q_target.l1.weight, tgt0)
     assert agent.memory.size == 8 * B          # ring of 9 slots: 8 complete transitions per env
+
+
+def test_two_gpu_data_parallel_loop(cuda):
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "run_dqn.py"), "--side", "32", "--envs", "512",
+           "--steps", "12", "--hidden", "256", "--check"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"replicas_identical": true' in r.stdout
