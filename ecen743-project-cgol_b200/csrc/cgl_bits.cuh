@@ -172,6 +172,77 @@ CGL_HD int8_t stable_update1_rule(int rule, int8_t s, bool prev, bool next, int8
     return 0;
 }
 
+// ---- bit-sliced int8 stability (32 cells per operation) -----------------------------------
+// For kernels that keep an env on chip for many steps the int8 plane is held as 8 bit planes per 32 cells
+// (plane b, bit j = bit b of cell j's byte): the rule then costs ~33 logic ops per 32 cells instead of ~100
+// with 4-cells-per-word bytes.  The price is a bit-matrix transpose on the way in and out.
+
+// 8x8 bit-matrix transpose (Hacker's Delight 7-3): byte r of x = row r  ->  byte c of the result = column c.
+CGL_HD uint64_t transpose8x8(uint64_t x)
+{
+    uint64_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+    return x;
+}
+
+// 4x4 byte transpose: out[i] byte k = in[k] byte i.
+CGL_HD void transpose4x4_bytes(const uint32_t (&a)[4], uint32_t (&o)[4])
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
+    const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+    o[0] = __byte_perm(t0, t1, 0x5410); o[1] = __byte_perm(t0, t1, 0x7632);
+    o[2] = __byte_perm(t2, t3, 0x5410); o[3] = __byte_perm(t2, t3, 0x7632);
+#else
+    for (int i = 0; i < 4; ++i) {
+        o[i] = 0;
+        for (int k = 0; k < 4; ++k) o[i] |= ((a[k] >> (8 * i)) & 0xffu) << (8 * k);
+    }
+#endif
+}
+
+// 32 int8 cells (8 words, cell j = byte j % 4 of word j / 4)  ->  8 bit planes.
+CGL_HD void bytes_to_planes32(const uint32_t (&w)[8], uint32_t (&p)[8])
+{
+    uint32_t lo[4], hi[4], pl[4], ph[4];
+    for (int k = 0; k < 4; ++k) {              // cells 8k..8k+7: byte b of the result = plane b of those cells
+        const uint64_t x = transpose8x8((uint64_t)w[2 * k] | ((uint64_t)w[2 * k + 1] << 32));
+        lo[k] = (uint32_t)x; hi[k] = (uint32_t)(x >> 32);
+    }
+    transpose4x4_bytes(lo, pl);
+    transpose4x4_bytes(hi, ph);
+    for (int b = 0; b < 4; ++b) { p[b] = pl[b]; p[4 + b] = ph[b]; }
+}
+
+CGL_HD void planes_to_bytes32(const uint32_t (&p)[8], uint32_t (&w)[8])
+{
+    const uint32_t pl[4] = {p[0], p[1], p[2], p[3]}, ph[4] = {p[4], p[5], p[6], p[7]};
+    uint32_t lo[4], hi[4];
+    transpose4x4_bytes(pl, lo);
+    transpose4x4_bytes(ph, hi);
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t x = transpose8x8((uint64_t)lo[k] | ((uint64_t)hi[k] << 32));
+        w[2 * k] = (uint32_t)x; w[2 * k + 1] = (uint32_t)(x >> 32);
+    }
+}
+
+// The base env's stability rule on bit planes: surv / born are 32-cell masks, spawn / stable_max the int8
+// constants.  surv: s == MAX ? s : s + 1 (ripple carry, wraps like int8);  born: SPAWN;  everything else: 0.
+CGL_HD void stable_update_sliced(uint32_t (&p)[8], uint32_t surv, uint32_t born, int spawn, int stable_max)
+{
+    uint32_t diff = 0;
+    for (int b = 0; b < 8; ++b) diff |= p[b] ^ (((stable_max >> b) & 1) ? 0xffffffffu : 0u);
+    uint32_t c = surv & diff;                                  // cells that increment
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t pb = p[b];
+        const uint32_t n = pb ^ c;
+        c &= pb;
+        p[b] = (surv & n) | (born & (((spawn >> b) & 1) ? 0xffffffffu : 0u));
+    }
+}
+
 // Expand a 4-bit nibble to 4 byte masks (bit i -> byte i = 0xFF).
 CGL_HD uint32_t nibble_to_bytemask(uint32_t nib)
 {

@@ -15,6 +15,8 @@
 // way out, so k steps cost 2.25/k bytes per cell-update instead of 2.25 and the loop is bound by the
 // integer pipe.  The per-step logic is the fused env kernel's (cgl_env.cu): bit-sliced rows, (born,
 // surv) nibbles through the lane-private mask tables, byte-SIMD stability update.
+#include <stdlib.h>
+
 #include "cgl_internal.cuh"
 
 namespace cgl {
@@ -228,6 +230,144 @@ env_run_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, ui
     }
 }
 
+// =========================================================================================
+// Bit-sliced variant for longer runs: the stability plane lives in REGISTERS as 8 bit planes per 32 cells
+// (cgl_bits.cuh), owned by the thread that owns the row; the rule is ~33 logic ops per 32 cells instead of
+// ~100 with bytes, the (born, surv) nibble plane and its barrier disappear (one barrier per step), and shared
+// memory only holds the two world bit planes.  The byte <-> bit-plane transposes on the way in and out cost
+// about four steps' worth of work, so cgl_env_run takes this kernel from max_steps >= 6.
+// =========================================================================================
+template <int S>
+struct SlicedCfg {
+    static constexpr int W = S / 32;
+    static constexpr int WPE = S * W;
+    static constexpr int SIZE = S * S;
+    static constexpr int TPE = (S <= 64) ? 32 : S;
+    static constexpr int EPC = (TPE >= 96) ? 1 : (128 / TPE);
+    static constexpr int THREADS = TPE * EPC;
+    static constexpr int RPB = S / TPE;
+    static constexpr int SMEM = EPC * (2 * WPE * 4) + EPC * 8;
+};
+
+template <int S>
+__global__ void __launch_bounds__(SlicedCfg<S>::THREADS)
+env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t n_envs,
+                      uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max,
+                      int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out,
+                      uint32_t *__restrict__ alive_out)
+{
+    using C = SlicedCfg<S>;
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const int g = threadIdx.x / C::TPE;
+    const int t = threadIdx.x % C::TPE;
+    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_dyn) + g * (2 * C::WPE);
+    uint32_t *nxt = cur + C::WPE;
+    int *red = reinterpret_cast<int *>(smem_dyn + C::EPC * (2 * C::WPE * 4)) + g * 2;
+    const uint32_t e = blockIdx.x * C::EPC + g;
+    const bool active = e < n_envs;
+
+    uint32_t pl[C::RPB][C::W][8];                   // this thread's rows: 8 bit planes per word
+    if (t == 0) { red[0] = 0; red[1] = 0; }
+    if (active) {
+        const uint4 *wp = reinterpret_cast<const uint4 *>(world_in + (size_t)e * C::WPE);
+        for (int i = t; i < C::WPE / 4; i += C::TPE) reinterpret_cast<uint4 *>(cur)[i] = wp[i];
+        const uint4 *sp = reinterpret_cast<const uint4 *>(stable + (size_t)e * C::SIZE);
+#pragma unroll
+        for (int j = 0; j < C::RPB; ++j)
+#pragma unroll
+            for (int w = 0; w < C::W; ++w) {
+                const uint4 a = sp[((t * C::RPB + j) * S + w * 32) / 16];
+                const uint4 b = sp[((t * C::RPB + j) * S + w * 32) / 16 + 1];
+                const uint32_t by[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                bytes_to_planes32(by, pl[j][w]);
+            }
+    }
+    __syncthreads();
+
+    auto env_vote = [&](bool p) -> bool {
+        if constexpr (C::EPC == 1) return __syncthreads_or(p) != 0;
+        const bool r = __any_sync(0xffffffffu, p);
+        __syncwarp();
+        return r;
+    };
+
+    uint32_t steps = 0;
+    bool done = !active || max_steps == 0;
+    while (!done) {
+        uint32_t changed = 0;
+        HSum hs[C::RPB + 2][C::W];
+        uint32_t cw[C::RPB + 2][C::W];
+#pragma unroll
+        for (int j = 0; j < C::RPB + 2; ++j) {
+            int r = t * C::RPB + j - 1;
+            r = r < 0 ? S - 1 : (r >= S ? 0 : r);
+            lds_words<C::W>(cur + r * C::W, cw[j]);
+#pragma unroll
+            for (int w = 0; w < C::W; ++w)
+                hs[j][w] = hsum(west_plane(cw[j][(w + C::W - 1) % C::W], cw[j][w]), cw[j][w],
+                                east_plane(cw[j][w], cw[j][(w + 1) % C::W]));
+        }
+#pragma unroll
+        for (int j = 0; j < C::RPB; ++j) {
+            uint32_t nx[C::W];
+#pragma unroll
+            for (int w = 0; w < C::W; ++w) {
+                const uint32_t c = cw[j + 1][w];
+                const uint32_t n = life_rule(hs[j][w], hs[j + 1][w], hs[j + 2][w], c);
+                nx[w] = n;
+                changed |= n ^ c;
+                stable_update_sliced(pl[j][w], n & c, n & ~c, spawn, stable_max);
+            }
+            sts_words<C::W>(nxt + (t * C::RPB + j) * C::W, nx);
+        }
+        const bool any_changed = env_vote(changed != 0);     // the only barrier of the step
+        uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+        ++steps;
+        done = steps >= max_steps || (stop_when_fixed && !any_changed);
+    }
+
+    int acc = 0;
+    uint32_t pop = 0;
+    if (active) {
+        uint4 *wo = reinterpret_cast<uint4 *>(world_out + (size_t)e * C::WPE);
+        for (int i = t; i < C::WPE / 4; i += C::TPE) {
+            const uint4 v = reinterpret_cast<const uint4 *>(cur)[i];
+            pop += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+            wo[i] = v;
+        }
+        uint4 *sp = reinterpret_cast<uint4 *>(stable + (size_t)e * C::SIZE);
+#pragma unroll
+        for (int j = 0; j < C::RPB; ++j)
+#pragma unroll
+            for (int w = 0; w < C::W; ++w) {
+                // reward = sum of int8 values = sum_b 2^b popc(plane b), the sign plane weighing -128
+#pragma unroll
+                for (int b = 0; b < 7; ++b) acc += __popc(pl[j][w][b]) << b;
+                acc -= __popc(pl[j][w][7]) << 7;
+                uint32_t by[8];
+                planes_to_bytes32(pl[j][w], by);
+                sp[((t * C::RPB + j) * S + w * 32) / 16] = make_uint4(by[0], by[1], by[2], by[3]);
+                sp[((t * C::RPB + j) * S + w * 32) / 16 + 1] = make_uint4(by[4], by[5], by[6], by[7]);
+            }
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    pop = __reduce_add_sync(0xffffffffu, pop);
+    if constexpr (C::EPC == 1) {
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&red[0], acc);
+            atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
+        }
+        __syncthreads();
+        acc = red[0];
+        pop = (uint32_t)red[1];
+    }
+    if (active && t == 0) {
+        if (reward_out != nullptr) reward_out[e] = acc;
+        if (alive_out != nullptr) alive_out[e] = pop;
+        if (steps_out != nullptr) steps_out[e] = (int32_t)steps;
+    }
+}
+
 // Any side whose three byte planes fit in shared memory (side <= 270): one CTA per env, one byte per cell.
 __global__ void __launch_bounds__(256)
 env_run_generic_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t side, uint32_t W,
@@ -299,6 +439,19 @@ env_run_generic_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *st
     }
 }
 
+// CGL_RUN_IMPL=bytes | sliced forces one kernel (tests, tuning); default: sliced from 6 steps on.
+static bool run_use_sliced(uint32_t max_steps)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char *v = getenv("CGL_RUN_IMPL");
+        forced = (v && v[0] == 'b') ? 1 : (v && v[0] == 's') ? 2 : 0;
+    }
+    if (forced == 1) return false;
+    if (forced == 2) return true;
+    return max_steps >= 6;
+}
+
 template <int S>
 static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t max_steps,
                           int stop, int spawn, int stable_max, int32_t *steps, int32_t *reward, uint32_t *alive,
@@ -311,8 +464,14 @@ static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, u
         configured = true;
     }
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
-    env_run_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, stop,
-                                                        rep4(spawn), rep4(stable_max), steps, reward, alive);
+    if (run_use_sliced(max_steps)) {
+        using D = SlicedCfg<S>;
+        env_run_sliced_kernel<S><<<grid, D::THREADS, D::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps,
+                                                                   stop, spawn, stable_max, steps, reward, alive);
+    } else {
+        env_run_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, stop,
+                                                            rep4(spawn), rep4(stable_max), steps, reward, alive);
+    }
     CGL_LAUNCH_CHECK();
     return 0;
 }

@@ -141,3 +141,24 @@ def test_generic_life_rectangles_vs_oracle(twin, rows, cols, wrap):
                         full = full + sh
             cells = (((full == 3) | ((full == 2) & (padded == 1))).astype(np.uint8))[1:-1]
         assert np.array_equal(unpack(twin, w, 1, rows, cols).reshape(rows, cols), cells)
+
+
+@pytest.mark.parametrize("spawn,smax", [(-2, 2), (-128, 127), (5, 127), (100, 120), (0, 0), (-1, -1), (7, -3)])
+def test_bit_sliced_stability_equals_scalar_rule(twin, spawn, smax):
+    """cgl_bits.cuh: byte <-> bit-plane transposes are exact inverses and the 32-cells-per-op rule equals the
+    scalar rule for every int8 value under every transition."""
+    twin.twin_sliced_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+    twin.twin_sliced_mismatches.restype = ctypes.c_uint64
+    rs = np.random.RandomState(abs(spawn) + 3)
+    # all 256 values x 3 transitions, each at a random position among random neighbours, plus pure random groups
+    groups = 256 * 3 + 500
+    cells = rs.randint(-128, 128, size=(groups, 32)).astype(np.int8)
+    tr = rs.randint(0, 3, size=(groups, 32)).astype(np.uint8)
+    for v in range(256):
+        for t in range(3):
+            g = v * 3 + t
+            pos = rs.randint(32)
+            cells[g, pos] = np.int8(v - 128)
+            tr[g, pos] = t
+    cells[768:800] = np.int8(smax)                      # whole groups at the ceiling
+    assert twin.twin_sliced_mismatches(P(cells), P(tr), groups, spawn, smax) == 0

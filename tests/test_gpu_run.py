@@ -86,10 +86,11 @@ def test_converge_batch_matches_oracle_env_by_env(cuda, side, n_envs, limit):
             assert len(seen) >= 3                               # the batch really had different trip counts
 
 
+@pytest.mark.parametrize("k", [3, 9])          # 3: the byte kernel, 9: the bit-sliced kernel (cgl_env_run.cu)
 @pytest.mark.parametrize("side", [32, 64, 96, 128, 160, 192, 224, 256, 5, 33, 100])
-def test_run_k_equals_k_steps(cuda, side):
+def test_run_k_equals_k_steps(cuda, side, k):
     from cgl_b200.batched import BatchedSim
-    n_envs, k = (7 if side <= 128 else 3), 9
+    n_envs = 7 if side <= 128 else 3
     a = BatchedSim(n_envs, side, seed=side, spawnStabilityFactor=-2, stableStabilityFactor=2, rng="device")
     b = BatchedSim(n_envs, side, seed=side, spawnStabilityFactor=-2, stableStabilityFactor=2, rng="device")
     for _ in range(k):
@@ -155,3 +156,15 @@ def test_facade_run_and_breakdown(cuda):
         ref.step()
     assert np.array_equal(env.get_state(vector=True), ref.world) and np.array_equal(env.get_stable(vector=True), ref.stable)
     assert int(env.reward()) == int(ref.reward())
+
+
+@pytest.mark.parametrize("impl", ["bytes", "sliced"])
+def test_both_run_kernels_reproduce_reference_vectors(cuda, impl):
+    """The two in-SM kernels are selected by step count; here each one is forced for every recorded case."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CGL_RUN_IMPL=impl)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_run_reproduces_reference_vectors or test_converge_batch_matches_oracle_env_by_env"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -176,4 +176,33 @@ uint64_t twin_rule_mismatches(int rule, int spawn, int stable_max, int empty, in
     return bad;
 }
 
+// Bit-sliced stability: transpose round trip and the sliced rule against the scalar rule, on `n_words`
+// groups of 32 cells with the given int8 values and transitions (tr: 0 survive, 1 born, 2 dead).
+uint64_t twin_sliced_mismatches(const int8_t *cells, const uint8_t *tr, uint64_t n_groups, int spawn, int stable_max)
+{
+    uint64_t bad = 0;
+    for (uint64_t g = 0; g < n_groups; ++g) {
+        uint32_t w[8], p[8], back[8], surv = 0, born = 0;
+        memcpy(w, cells + 32 * g, 32);
+        bytes_to_planes32(w, p);
+        for (int j = 0; j < 32; ++j)
+            for (int b = 0; b < 8; ++b)
+                bad += ((p[b] >> j) & 1u) != (((uint8_t)cells[32 * g + j] >> b) & 1u);
+        planes_to_bytes32(p, back);
+        bad += memcmp(back, w, 32) != 0;
+        for (int j = 0; j < 32; ++j) {
+            if (tr[32 * g + j] == 0) surv |= 1u << j;
+            if (tr[32 * g + j] == 1) born |= 1u << j;
+        }
+        stable_update_sliced(p, surv, born, spawn, stable_max);
+        planes_to_bytes32(p, back);
+        for (int j = 0; j < 32; ++j) {
+            const int8_t want = stable_update1(cells[32 * g + j], tr[32 * g + j] == 0, tr[32 * g + j] != 2,
+                                               (int8_t)spawn, (int8_t)stable_max);
+            bad += ((const int8_t *)back)[j] != want;
+        }
+    }
+    return bad;
+}
+
 }  // extern "C"
