@@ -252,15 +252,15 @@ class BatchedSim:
         max_steps, the number of steps the batch was asked for."""
         if not isinstance(max_steps, int) or max_steps < 0:
             raise ValueError("max_steps must be a non-negative integer")
-        if DEAD_RULES[self.dead_rule] != 0:
-            raise native.CglNativeError("run() implements the base env's rule only (dead_rule='zero')")
         steps = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_env_run(native.dptr(self._wa), native.dptr(self._wa), native.dptr(self.stable),
-                                               self.n_envs, self.side, max_steps, int(until_fixed), self.spawn,
-                                               self.stable_max, native.dptr(steps), native.dptr(self._reward),
-                                               native.dptr(self._alive) if want_alive else None, self._stream()),
-                         "cgl_env_run")
+            native.check(self._lib.cgl_env_run_rule(native.dptr(self._wa), native.dptr(self._wa),
+                                                    native.dptr(self.stable), self.n_envs, self.side, max_steps,
+                                                    int(until_fixed), self.spawn, self.stable_max,
+                                                    DEAD_RULES[self.dead_rule], self.empty, self.empty_min,
+                                                    native.dptr(steps), native.dptr(self._reward),
+                                                    native.dptr(self._alive) if want_alive else None, self._stream()),
+                         "cgl_env_run_rule")
         self.count += max_steps
         self.launches += 1
         return self.stable, self._reward, steps

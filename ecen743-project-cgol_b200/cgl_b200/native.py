@@ -38,6 +38,7 @@ SIGNATURES = {
     "cgl_env_step": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "cgl_env_step_chained": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "cgl_env_run": (_i, [_vp, _vp, _vp, _u64, _u32, _u32, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cgl_env_run_rule": (_i, [_vp, _vp, _vp, _u64, _u32, _u32, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cgl_breakdown_stable": (_i, [_vp, _u64, _u64, _vp, _vp]),
     "cgl_env_step_rule": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "cgl_toggle_rule": (_i, [_vp, _vp, _u64, _u32, _vp, _u32, _i, _i, _vp, _vp]),

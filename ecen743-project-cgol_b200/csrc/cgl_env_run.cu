@@ -87,7 +87,8 @@ template <int S>
 __global__ void __launch_bounds__(RunCfg<S>::THREADS)
 env_run_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t n_envs,
                uint32_t max_steps, int stop_when_fixed, uint32_t spawn4, uint32_t max4,
-               int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out)
+               int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
+               int rule, uint32_t min4, uint32_t empty4)
 {
     using C = RunCfg<S>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -182,8 +183,13 @@ env_run_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, ui
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t surv_mask = lds32(__byte_perm(sv, lane_s, 0x5504 + 16 * k));
-                const uint32_t born_spawn = lds32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
-                s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
+                if (rule == CGL_DEAD_ZERO) {
+                    const uint32_t born_spawn = lds32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
+                    s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
+                } else {                    // the CGL_action+ fork's dead-cell rules (cgl_bits.cuh)
+                    const uint32_t born_mask = lds32(__byte_perm(bn, lane_s, 0x5504 + 16 * k));
+                    s[k] = stable_update4_rule(rule, s[k], surv_mask, born_mask, spawn4, max4, min4, empty4);
+                }
             }
             sst[c] = make_uint4(s[0], s[1], s[2], s[3]);
         }
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(256)
 env_run_generic_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t side, uint32_t W,
                        uint32_t max_steps, int stop_when_fixed, int8_t spawn, int8_t stable_max,
                        int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out,
-                       uint32_t *__restrict__ alive_out)
+                       uint32_t *__restrict__ alive_out, int rule, int8_t empty, int8_t empty_min)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const uint32_t size = side * side;
@@ -405,7 +411,7 @@ env_run_generic_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *st
             const uint8_t q = (n == 3u) || (n == 2u && p);
             b[i] = q;
             changed |= (p != q);
-            st[i] = stable_update1(st[i], p != 0, q != 0, spawn, stable_max);
+            st[i] = stable_update1_rule(rule, st[i], p != 0, q != 0, spawn, stable_max, empty, empty_min);
         }
         const bool any_changed = __syncthreads_or(changed) != 0;
         uint8_t *tmp = a; a = b; b = tmp;
@@ -455,7 +461,7 @@ static bool run_use_sliced(uint32_t max_steps)
 template <int S>
 static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t max_steps,
                           int stop, int spawn, int stable_max, int32_t *steps, int32_t *reward, uint32_t *alive,
-                          cudaStream_t st)
+                          cudaStream_t st, int rule, int empty, int empty_min)
 {
     using C = RunCfg<S>;
     static bool configured = false;
@@ -464,13 +470,14 @@ static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, u
         configured = true;
     }
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
-    if (run_use_sliced(max_steps)) {
+    if (rule == CGL_DEAD_ZERO && run_use_sliced(max_steps)) {      // the bit-sliced kernel knows the base rule only
         using D = SlicedCfg<S>;
         env_run_sliced_kernel<S><<<grid, D::THREADS, D::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps,
                                                                    stop, spawn, stable_max, steps, reward, alive);
     } else {
         env_run_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, stop,
-                                                            rep4(spawn), rep4(stable_max), steps, reward, alive);
+                                                            rep4(spawn), rep4(stable_max), steps, reward, alive, rule,
+                                                            rep4(empty_min), rep4(empty));
     }
     CGL_LAUNCH_CHECK();
     return 0;
@@ -500,18 +507,22 @@ breakdown_kernel(const int8_t *__restrict__ stable, uint64_t size, uint32_t *__r
 
 using namespace cgl;
 
-extern "C" int cgl_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
-                           uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max, int32_t *steps,
-                           int32_t *reward, uint32_t *alive, cgl_stream_t stream)
+extern "C" int cgl_env_run_rule(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
+                                uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max, int dead_rule,
+                                int empty, int empty_min, int32_t *steps, int32_t *reward, uint32_t *alive,
+                                cgl_stream_t stream)
 {
     CGL_REQUIRE(win && wout && stable && n_envs && side, CGL_E_BADARG, "cgl_env_run: bad argument");
     CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_run: n_envs too large");
+    CGL_REQUIRE(dead_rule >= CGL_DEAD_ZERO && dead_rule <= CGL_DEAD_SAT && empty >= -128 && empty <= 127 &&
+                    empty_min >= -128 && empty_min <= 127,
+                CGL_E_BADARG, "cgl_env_run_rule: dead_rule must be 0..2, empty / empty_min must fit int8");
     cudaStream_t st = as_stream(stream);
     if (cgl_env_step_is_fused(side)) {
 #define CGL_CASE(S)                                                                                       \
     case S:                                                                                               \
         return launch_env_run<S>(win, wout, stable, n_envs, max_steps, stop_when_fixed, spawn, stable_max, \
-                                 steps, reward, alive, st)
+                                 steps, reward, alive, st, dead_rule, empty, empty_min)
         switch (side) {
             CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
             CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
@@ -528,9 +539,18 @@ extern "C" int cgl_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, 
     }
     env_run_generic_kernel<<<(unsigned)n_envs, 256, smem, st>>>(win, wout, stable, side, cgl_words_per_row(side),
                                                                max_steps, stop_when_fixed, (int8_t)spawn,
-                                                               (int8_t)stable_max, steps, reward, alive);
+                                                               (int8_t)stable_max, steps, reward, alive, dead_rule,
+                                                               (int8_t)empty, (int8_t)empty_min);
     CGL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int cgl_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
+                           uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max, int32_t *steps,
+                           int32_t *reward, uint32_t *alive, cgl_stream_t stream)
+{
+    return cgl_env_run_rule(win, wout, stable, n_envs, side, max_steps, stop_when_fixed, spawn, stable_max,
+                            CGL_DEAD_ZERO, 0, 0, steps, reward, alive, stream);
 }
 
 extern "C" int cgl_breakdown_stable(const int8_t *stable, uint64_t n_envs, uint64_t size, uint32_t *hist_out,

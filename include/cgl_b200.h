@@ -127,6 +127,13 @@ int cgl_env_run(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *s
                 uint32_t side, uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max,
                 int32_t *steps_out_dev, int32_t *reward_out_dev, uint32_t *alive_out_dev, cgl_stream_t stream);
 
+/* cgl_env_run with the CGL_action+ fork's dead-cell rule (dead_rule / empty / empty_min as in
+ * cgl_env_step_rule) -- the fork's validate.py convergence loop runs on the fork's env. */
+int cgl_env_run_rule(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev, uint64_t n_envs,
+                     uint32_t side, uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max,
+                     int dead_rule, int empty, int empty_min, int32_t *steps_out_dev, int32_t *reward_out_dev,
+                     uint32_t *alive_out_dev, cgl_stream_t stream);
+
 /* Value counts of the stability plane, the device form of breakdown_stable (CGL/CGL_action+/CGL.py:
  * 294-297, np.unique(..., return_counts=True)): hist_out_dev uint32 [n_envs][256],
  * hist[e][v + 128] = number of cells of env e whose stability equals v. */

@@ -102,6 +102,46 @@ def main():
     trace("fused128", out, make_sim(side=128, seed=3, spawnStabilityFactor=-2, stableStabilityFactor=2, empty=-1, empty_min=-3),
           [7, None, 128 * 128, 16383])
     np.savez_compressed(os.path.join(HERE, "golden_action_plus.npz"), **out)
+    converge_cases()
+
+
+def converge_cases():
+    """The fork's validation loop (CGL_action+/validate.py:133-139) on the fork's env, statement for statement;
+    also plain step loops.  Output: golden_action_plus_converge.json."""
+    import hashlib
+    import json
+    cases = []
+    for mode, side, seed, spawn, stable, empty, emin, limit in [
+            ("converge", 10, 0, -2, 2, 0, -128, 300), ("converge", 10, 1, -2, 2, -1, -5, 300),
+            ("converge", 10, 5, -2, 2, -1, -5, 300), ("converge", 16, 3, -2, 2, -2, -9, 400),
+            ("converge", 7, 0, -2, 3, 3, 7, 100), ("converge", 32, 0, -2, 2, -1, -4, 120),
+            ("converge", 33, 1, -2, 2, -1, -4, 60), ("converge", 64, 0, -2, 2, -1, -3, 30),
+            ("steps", 32, 1, -2, 2, -1, -6, 40), ("steps", 128, 0, -2, 2, 0, -128, 6), ("steps", 12, 3, -1, 1, -3, -20, 50)]:
+        env = make_sim(side=side, seed=seed, spawnStabilityFactor=spawn, stableStabilityFactor=stable, empty=empty,
+                       empty_min=emin)
+        steps = 0
+        if mode == "converge":
+            old = env.get_state()
+            env.step()
+            steps = 1
+            count_down = limit
+            while not env.match(old) and count_down:
+                old = env.get_state()
+                env.step()
+                steps += 1
+                count_down -= 1
+        else:
+            for _ in range(limit):
+                env.step()
+            steps = limit
+        cases.append({"mode": mode, "side": side, "seed": seed, "spawn": spawn, "stable": stable, "empty": empty,
+                      "empty_min": emin, "limit": limit, "steps": steps, "stability": int(env.stability()),
+                      "alive": int(env.alive()), "world_sha": hashlib.sha256(env.world.tobytes()).hexdigest(),
+                      "stable_sha": hashlib.sha256(env.stable.tobytes()).hexdigest(),
+                      "breakdown": [[int(v) for v in row] for row in env.breakdown_stable()]})
+        print(mode, side, seed, "steps", steps, "alive", cases[-1]["alive"], file=sys.stderr)
+    with open(os.path.join(HERE, "golden_action_plus_converge.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden_action_plus.py", "cases": cases}, f, indent=1)
 
 
 if __name__ == "__main__":

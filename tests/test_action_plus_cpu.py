@@ -114,3 +114,23 @@ def test_dead_zero_rule_is_the_base_env():
         oracle.step(a_w, a_s, side, -2, 2)
         oracle.step_rule(b_w, b_s, side, -2, 2, oracle.DEAD_ZERO)
         assert np.array_equal(a_w, b_w) and np.array_equal(a_s, b_s)
+
+
+import hashlib  # noqa: E402
+import json  # noqa: E402
+
+with open(os.path.join(ROOT, "tests", "golden", "golden_action_plus_converge.json")) as _f:
+    FORK_RUNS = json.load(_f)["cases"]
+
+
+@pytest.mark.parametrize("c", FORK_RUNS, ids=lambda c: f"{c['mode']}-side{c['side']}-seed{c['seed']}")
+def test_oracle_run_rule_matches_the_forks_loops(c):
+    """validate.py:133-139 / plain step loops recorded from the fork's CPU back end."""
+    world = oracle.initial_world(c["side"], c["seed"])
+    stable = oracle.initial_stable_fork(world, c["spawn"], c["empty"])
+    n = oracle.run_rule(world, stable, c["side"], c["spawn"], c["stable"], c["limit"] + (c["mode"] == "converge"),
+                        oracle.DEAD_SAT, c["empty"], c["empty_min"], until_fixed=c["mode"] == "converge")
+    assert n == c["steps"] and int(oracle.reward(stable)) == c["stability"] and int(oracle.alive(world)) == c["alive"]
+    assert hashlib.sha256(world.tobytes()).hexdigest() == c["world_sha"]
+    assert hashlib.sha256(stable.tobytes()).hexdigest() == c["stable_sha"]
+    assert oracle.breakdown(stable).tolist() == c["breakdown"]

@@ -214,3 +214,51 @@ def test_fork_facade_api(fork):
                      (dict(empty=300), OverflowError), (dict(dead_rule="zero"), ValueError)):
         with pytest.raises(exc):
             fork.sim(side=4, gpu=True, **bad)
+
+
+import hashlib  # noqa: E402
+import json  # noqa: E402
+
+from conftest import ROOT  # noqa: E402
+
+with open(os.path.join(ROOT, "tests", "golden", "golden_action_plus_converge.json")) as _f:
+    FORK_RUNS = json.load(_f)["cases"]
+
+
+@pytest.mark.parametrize("c", FORK_RUNS, ids=lambda c: f"{c['mode']}-side{c['side']}-seed{c['seed']}")
+def test_run_on_the_fork_env_reproduces_the_forks_loops(cuda, c):
+    from cgl_b200.batched import BatchedSim
+    env = BatchedSim(1, c["side"], seed=c["seed"], spawnStabilityFactor=c["spawn"], stableStabilityFactor=c["stable"],
+                     dead_rule="sat", empty=c["empty"], empty_min=c["empty_min"], masked_toggle=True)
+    conv = c["mode"] == "converge"
+    obs, rew, steps = env.run(c["limit"] + conv, until_fixed=conv, want_alive=True)
+    assert int(steps.item()) == c["steps"] and int(rew.item()) == c["stability"]
+    assert int(env.last_alive().item()) == c["alive"]
+    assert hashlib.sha256(env.get_state().cpu().numpy().tobytes()).hexdigest() == c["world_sha"]
+    assert hashlib.sha256(obs.cpu().numpy().tobytes()).hexdigest() == c["stable_sha"]
+    hist = env.breakdown_stable()[0].cpu().numpy()
+    vals = np.nonzero(hist)[0]
+    assert [(vals - 128).tolist(), hist[vals].tolist()] == c["breakdown"]
+
+
+@pytest.mark.parametrize("rule", ["decay", "sat"])
+@pytest.mark.parametrize("side,k", [(128, 5), (64, 12), (32, 7), (96, 4), (20, 9)])
+def test_fork_run_k_equals_k_steps(cuda, rule, side, k):
+    from cgl_b200.batched import BatchedSim
+    kw = dict(seed=side, spawnStabilityFactor=-2, stableStabilityFactor=3, rng="device", dead_rule=rule, empty=-1,
+              empty_min=-7, masked_toggle=True)
+    a, b = BatchedSim(9, side, **kw), BatchedSim(9, side, **kw)
+    for _ in range(k):
+        oa, ra, _ = a.step(None, want_alive=True)
+    ob, rb, steps = b.run(k, want_alive=True)
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(a.world, b.world)
+    assert torch.equal(a.last_alive(), b.last_alive()) and bool((steps == k).all())
+
+
+def test_fork_facade_run(fork):
+    c = next(x for x in FORK_RUNS if x["mode"] == "converge" and x["side"] == 10 and x["seed"] == 1)
+    env = fork.sim(side=10, seed=1, gpu=True, spawnStabilityFactor=c["spawn"], stableStabilityFactor=c["stable"],
+                   empty=c["empty"], empty_min=c["empty_min"], dead_rule="sat")
+    assert env.run(c["limit"] + 1, until_fixed=True) == c["steps"]
+    assert int(env.stability()) == c["stability"] and int(env.alive()) == c["alive"]
+    assert env.breakdown_stable().tolist() == c["breakdown"]
