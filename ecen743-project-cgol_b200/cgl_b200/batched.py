@@ -399,10 +399,15 @@ class BatchedSim:
 
     # ------------------------------------------------------------------ host-buffer step (e2e)
     def step_host(self, actions_host: torch.Tensor | None, reward_host: torch.Tensor,
-                  obs_host: torch.Tensor | None = None) -> None:
+                  obs_host: torch.Tensor | None = None, sync: bool = True, stream: int | None = None) -> None:
         """The same step driven from HOST buffers: actions int32 [B] (pinned) are copied H2D, the
         step runs, reward int32 [B] (and the int8 observation if obs_host is given) come back D2H;
-        returns after the copies completed.  One C-ABI call: cgl_env_step_host."""
+        returns after the copies completed.  One C-ABI call: cgl_env_step_host.
+
+        sync=False (cgl_env_step_host_async) returns once everything is enqueued on the current stream; call
+        wait_host() on the same stream before reading reward_host / obs_host or rewriting actions_host.  Two
+        BatchedSim groups on two streams then overlap one group's host round trip with the other's step.
+        stream: a raw cudaStream_t (e.g. torch.cuda.Stream().cuda_stream) instead of torch's current stream."""
         if self._ext:
             raise native.CglNativeError("step_host() implements the base env only (dead_rule='zero', unmasked toggle)")
         key = (0 if actions_host is None else actions_host.data_ptr(), reward_host.data_ptr(),
@@ -421,9 +426,17 @@ class BatchedSim:
             self._n_launch_host[key] = self._lib.cgl_env_step_launches(self.side, int(actions_host is not None))
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
-        rc = self._lib.cgl_env_step_host(*args, self._stream())
+        rc = (self._lib.cgl_env_step_host if sync else self._lib.cgl_env_step_host_async)(
+            *args, self._stream() if stream is None else stream)
         if rc:
             native.check(rc, "cgl_env_step_host")
         self._wa, self._wb = self._wb, self._wa
         self.count += 1
         self.launches += self._n_launch_host[key]
+
+    def wait_host(self, stream: int | None = None) -> None:
+        """Block until everything enqueued on the stream (step_host(sync=False)) has completed."""
+        rc = self._lib.cgl_stream_wait(self._stream() if stream is None else stream)
+        if rc:
+            native.check(rc, "cgl_stream_wait")
+

@@ -54,6 +54,8 @@ SIGNATURES = {
     "cgl_match": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "cgl_step_state_gpu": (_i, [_vp, _vp, _u32, _i, _i]),
     "cgl_env_step_host": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "cgl_env_step_host_async": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "cgl_stream_wait": (_i, [_vp]),
     "cgl_ipc_get_handle": (_i, [_vp, _vp]),
     "cgl_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),
     "cgl_ipc_close_handle": (_i, [_vp]),

@@ -189,10 +189,10 @@ extern "C" int cgl_step_state_gpu(uint8_t *world_host, int8_t *stable_host, uint
     return 0;
 }
 
-extern "C" int cgl_env_step_host(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
-                                 uint32_t side, const int32_t *actions_host, int32_t *actions_dev,
-                                 int spawn, int stable_max, int32_t *reward_dev, int32_t *reward_host,
-                                 int8_t *obs_host, cgl_stream_t stream)
+static int env_step_host_impl(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                              uint32_t side, const int32_t *actions_host, int32_t *actions_dev,
+                              int spawn, int stable_max, int32_t *reward_dev, int32_t *reward_host,
+                              int8_t *obs_host, cgl_stream_t stream, bool sync)
 {
     CGL_REQUIRE(win && wout && stable && n_envs && side, CGL_E_BADARG, "cgl_env_step_host: bad argument");
     CGL_REQUIRE(!actions_host || actions_dev, CGL_E_BADARG, "cgl_env_step_host: actions scratch missing");
@@ -221,9 +221,37 @@ extern "C" int cgl_env_step_host(uint32_t *win, uint32_t *wout, int8_t *stable, 
         CGL_CUDA(cudaMemcpyAsync(reward_host, reward_dev, n_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (obs_host)
         CGL_CUDA(cudaMemcpyAsync(obs_host, stable, n_envs * (uint64_t)side * side, cudaMemcpyDeviceToHost, st));
-    CGL_CUDA(cudaStreamSynchronize(st));
+    if (sync) CGL_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+
+extern "C" int cgl_env_step_host(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                                 uint32_t side, const int32_t *actions_host, int32_t *actions_dev,
+                                 int spawn, int stable_max, int32_t *reward_dev, int32_t *reward_host,
+                                 int8_t *obs_host, cgl_stream_t stream)
+{
+    return env_step_host_impl(win, wout, stable, n_envs, side, actions_host, actions_dev, spawn, stable_max,
+                              reward_dev, reward_host, obs_host, stream, true);
+}
+
+// Same, without the final synchronisation: the caller waits with cgl_stream_wait (or any stream sync) before it
+// reads reward_host / obs_host or overwrites actions_host.  Two env groups on two streams then overlap one
+// group's host round trip with the other group's step.
+extern "C" int cgl_env_step_host_async(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
+                                       uint32_t side, const int32_t *actions_host, int32_t *actions_dev,
+                                       int spawn, int stable_max, int32_t *reward_dev, int32_t *reward_host,
+                                       int8_t *obs_host, cgl_stream_t stream)
+{
+    return env_step_host_impl(win, wout, stable, n_envs, side, actions_host, actions_dev, spawn, stable_max,
+                              reward_dev, reward_host, obs_host, stream, false);
+}
+
+extern "C" int cgl_stream_wait(cgl_stream_t stream)
+{
+    CGL_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return 0;
+}
+
 
 // ---- IPC + halo ------------------------------------------------------------------------------
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -226,6 +226,18 @@ int cgl_env_step_host(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *s
                       int32_t *reward_dev_scratch, int32_t *reward_host, int8_t *obs_host,
                       cgl_stream_t stream);
 
+/* cgl_env_step_host without the final synchronisation: returns as soon as the copies and the step are
+ * enqueued on `stream`.  The caller calls cgl_stream_wait(stream) (or any stream synchronisation) before it
+ * reads reward_host / obs_host or overwrites actions_host.  Splitting the environments into two groups on two
+ * streams overlaps one group's host round trip (result read, next actions, enqueue) with the other group's
+ * step -- the usual double-buffered rollout. */
+int cgl_env_step_host_async(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev,
+                            uint64_t n_envs, uint32_t side, const int32_t *actions_host,
+                            int32_t *actions_dev_scratch, int spawn, int stable_max,
+                            int32_t *reward_dev_scratch, int32_t *reward_host, int8_t *obs_host,
+                            cgl_stream_t stream);
+int cgl_stream_wait(cgl_stream_t stream);
+
 /* ---- CUDA IPC helpers for the row-band halo exchange over NVLink (multi-GPU life mode) ----
  * One process per GPU; each rank exports its ghost-row buffer and maps its neighbours'. */
 int cgl_ipc_get_handle(void *dev_ptr, uint8_t handle_out[64]);

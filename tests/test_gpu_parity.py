@@ -403,3 +403,34 @@ def test_facade_reference_attributes(cgl):
     w = env.get_state(vector=True)
     assert np.array_equal(w, tr.worlds[1])
     assert env.get_stable(vector=True)[tr.action(1)] == tr.spawn or tr.action(1) == 100   # ... but stable = spawn
+
+
+def test_async_host_step_two_groups_equal_sync_steps(cgl):
+    """cgl_env_step_host_async + cgl_stream_wait: two env groups on two streams, double-buffered, give the same
+    observations and rewards as synchronous host steps of the same envs."""
+    from cgl_b200.batched import BatchedSim
+    side, n = 64, 96
+    size = side * side
+    rs = np.random.RandomState(4)
+    sync_env = BatchedSim(2 * n, side, seed=9, spawnStabilityFactor=-2, stableStabilityFactor=2)
+    groups = [BatchedSim(n, side, seed=9, first_env=g * n, spawnStabilityFactor=-2, stableStabilityFactor=2) for g in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    acts_all = torch.empty(2 * n, dtype=torch.int32).pin_memory()
+    rew_all = torch.empty(2 * n, dtype=torch.int32).pin_memory()
+    acts_g = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    rew_g = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    torch.cuda.synchronize()
+    for t in range(6):
+        a = rs.randint(0, size + 1, size=2 * n).astype(np.int32)
+        acts_all.numpy()[:] = a
+        sync_env.step_host(acts_all, rew_all)
+        for g in range(2):
+            with torch.cuda.stream(streams[g]):
+                groups[g].wait_host()
+                acts_g[g].numpy()[:] = a[g * n:(g + 1) * n]
+                groups[g].step_host(acts_g[g], rew_g[g], sync=False)
+        for g in range(2):
+            with torch.cuda.stream(streams[g]):
+                groups[g].wait_host()
+            assert np.array_equal(rew_g[g].numpy(), rew_all.numpy()[g * n:(g + 1) * n]), (t, g)
+            assert torch.equal(groups[g].stable, sync_env.stable[g * n:(g + 1) * n])
