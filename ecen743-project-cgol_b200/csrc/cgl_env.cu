@@ -339,9 +339,12 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     using C = EnvCfg<S>;
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
     static int pad = -1;                        // tuning knob: extra dynamic smem limits CTAs/SM
+    static PerDeviceOnce once;
     if (pad < 0) {
         const char *v = getenv("CGL_ENV_SMEM_PAD");
         pad = v ? atoi(v) : 0;
+    }
+    if (once.first()) {
         CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
         CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, false>,

@@ -464,11 +464,9 @@ static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, u
                           cudaStream_t st, int rule, int empty, int empty_min)
 {
     using C = RunCfg<S>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first())
         CGL_CUDA(cudaFuncSetAttribute(env_run_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        configured = true;
-    }
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
     if (rule == CGL_DEAD_ZERO && run_use_sliced(max_steps)) {      // the bit-sliced kernel knows the base rule only
         using D = SlicedCfg<S>;
@@ -532,11 +530,9 @@ extern "C" int cgl_env_run_rule(const uint32_t *win, uint32_t *wout, int8_t *sta
     const size_t smem = 3ull * side * side;
     CGL_REQUIRE(smem <= 220 * 1024, CGL_E_BADARG,
                 "cgl_env_run: side must be a fused side or small enough for shared memory (side <= 273)");
-    static size_t configured = 0;
-    if (smem > configured) {
-        CGL_CUDA(cudaFuncSetAttribute(env_run_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static PerDeviceOnce once;                   // opt in to the largest size once per device
+    if (once.first())
+        CGL_CUDA(cudaFuncSetAttribute(env_run_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     env_run_generic_kernel<<<(unsigned)n_envs, 256, smem, st>>>(win, wout, stable, side, cgl_words_per_row(side),
                                                                max_steps, stop_when_fixed, (int8_t)spawn,
                                                                (int8_t)stable_max, steps, reward, alive, dead_rule,

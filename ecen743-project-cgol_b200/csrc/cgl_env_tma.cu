@@ -251,7 +251,8 @@ static int launch_env_tma(const uint32_t *win, uint32_t *wout, int8_t *stable, u
 {
     using C = TmaCfg<S, THREADS>;
     static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         CGL_CUDA(cudaFuncSetAttribute(env_step_tma_kernel<S, THREADS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         int n = 0;

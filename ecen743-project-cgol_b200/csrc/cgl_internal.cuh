@@ -40,6 +40,20 @@ int sm_count();
         }                                                                                   \
     } while (0)
 
+// Kernel attributes (cudaFuncSetAttribute) belong to the device that is current when they are set: a
+// process that drives several GPUs has to configure each of them once.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 static inline cudaStream_t as_stream(cgl_stream_t s) { return (cudaStream_t)s; }
 
 // grid size for a grid-stride kernel over `n` items with `threads` per block:
