@@ -397,6 +397,41 @@ class BatchedSim:
         self.launches += 3
         return bool(eq.item())
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, path) -> None:
+        """Write the whole batch to an .npz: the packed world plane (1 bit per cell, the device layout), the int8
+        stability plane and every constant needed to resume.  The per-env form in the reference's array format
+        is sim.save() (CGL/CGL.py:332-333); this is the batched, 8x smaller form of the same state."""
+        np.savez_compressed(
+            path, format=np.array("cgl_b200.batched.v1"), world=self._wa.cpu().numpy().view(np.uint32),
+            stable=self.stable.cpu().numpy(), init_world=self._init_world.cpu().numpy().view(np.uint32),
+            init_stable=self._init_stable.cpu().numpy(),
+            meta=np.array([self.n_envs, self.side, self.count, self.spawn, self.stable_max, DEAD_RULES[self.dead_rule],
+                           self.empty, self.empty_min, int(self.masked_toggle), self.seed, self.first_env], dtype=np.int64))
+
+    @classmethod
+    def load_checkpoint(cls, path, device="cuda") -> "BatchedSim":
+        """Rebuild a BatchedSim from save_checkpoint(); stepping it continues bit for bit where the saved one was."""
+        with np.load(path) as z:
+            if str(z["format"]) != "cgl_b200.batched.v1":
+                raise ValueError(f"{path}: not a cgl_b200 batched checkpoint")
+            n, side, count, spawn, smax, rule, empty, emin, masked, seed, first = (int(v) for v in z["meta"])
+            world, stable = z["world"], z["stable"]
+            init_world, init_stable = z["init_world"], z["init_stable"]
+        W = (side + 31) // 32
+        if world.shape != (n, side, W) or stable.shape != (n, side * side):
+            raise ValueError(f"{path}: plane shapes do not match the recorded batch ({n} envs, side {side})")
+        rule_name = {v: k for k, v in DEAD_RULES.items()}[rule]
+        env = cls(n, side, seed=seed, spawnStabilityFactor=spawn, stableStabilityFactor=smax, device=device,
+                  states=np.zeros((n, side * side), np.uint8), first_env=first, dead_rule=rule_name, empty=empty,
+                  empty_min=emin, masked_toggle=bool(masked))
+        env._wa.copy_(torch.from_numpy(world.view(np.int32)))
+        env.stable.copy_(torch.from_numpy(stable))
+        env._init_world.copy_(torch.from_numpy(init_world.view(np.int32)))
+        env._init_stable.copy_(torch.from_numpy(init_stable))
+        env.count = count
+        return env
+
     # ------------------------------------------------------------------ host-buffer step (e2e)
     def step_host(self, actions_host: torch.Tensor | None, reward_host: torch.Tensor,
                   obs_host: torch.Tensor | None = None, sync: bool = True, stream: int | None = None) -> None:

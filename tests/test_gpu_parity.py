@@ -434,3 +434,29 @@ def test_async_host_step_two_groups_equal_sync_steps(cgl):
                 groups[g].wait_host()
             assert np.array_equal(rew_g[g].numpy(), rew_all.numpy()[g * n:(g + 1) * n]), (t, g)
             assert torch.equal(groups[g].stable, sync_env.stable[g * n:(g + 1) * n])
+
+
+@pytest.mark.parametrize("kw", [dict(side=64), dict(side=10), dict(side=32, dead_rule="decay", empty=-1, empty_min=-5, masked_toggle=True)])
+def test_checkpoint_resume_continues_bit_for_bit(cgl, tmp_path, kw):
+    from cgl_b200.batched import BatchedSim
+    side = kw.pop("side")
+    n, size = 40, side * side
+    env = BatchedSim(n, side, seed=6, spawnStabilityFactor=-2, stableStabilityFactor=2, rng="device", **kw)
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    acts = [torch.randint(0, size + 1, (n,), dtype=torch.int32, device="cuda", generator=g) for _ in range(8)]
+    for a in acts[:3]:
+        env.step(a)
+    path = str(tmp_path / "batch.npz")
+    env.save_checkpoint(path)
+    twin = BatchedSim.load_checkpoint(path)
+    assert twin.count == env.count == 3 and twin.dead_rule == env.dead_rule and twin.masked_toggle == env.masked_toggle
+    assert torch.equal(twin.world, env.world) and torch.equal(twin.stable, env.stable)
+    for a in acts[3:]:
+        oa, ra, _ = env.step(a)
+        ob, rb, _ = twin.step(a)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(env.world, twin.world)
+    env.reset(); twin.reset()
+    assert torch.equal(env.world, twin.world) and torch.equal(env.stable, twin.stable)
+    with pytest.raises(ValueError):
+        np.savez(str(tmp_path / "bad.npz"), format=np.array("something else"))
+        BatchedSim.load_checkpoint(str(tmp_path / "bad.npz"))
