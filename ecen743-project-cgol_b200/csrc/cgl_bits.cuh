@@ -228,18 +228,33 @@ CGL_HD void planes_to_bytes32(const uint32_t (&p)[8], uint32_t (&w)[8])
     }
 }
 
-// The base env's stability rule on bit planes: surv / born are 32-cell masks, spawn / stable_max the int8
-// constants.  surv: s == MAX ? s : s + 1 (ripple carry, wraps like int8);  born: SPAWN;  everything else: 0.
-CGL_HD void stable_update_sliced(uint32_t (&p)[8], uint32_t surv, uint32_t born, int spawn, int stable_max)
+// p += k (mod 256) for all 32 cells, k a constant: ripple-carry addition of a uniform operand.
+CGL_HD void add_const_sliced(uint32_t (&p)[8], int k)
+{
+    uint32_t c = 0;
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t kb = ((k >> b) & 1) ? 0xffffffffu : 0u;
+        const uint32_t pb = p[b];
+        p[b] = pb ^ kb ^ c;
+        c = (pb & kb) | (c & (pb | kb));
+    }
+}
+
+// The base env's stability rule on bit planes in SPAWN-RELATIVE form: the planes hold u = s - SPAWN (mod 256)
+// for live cells and anything for dead ones (a dead cell's value is never read: a birth overwrites it and the
+// caller masks the planes with the world when it converts back).  Then a born cell is u = 0, exactly like a
+// dead one, and the whole rule is: survivors increment unless u == max_rel (= STABLE - SPAWN mod 256),
+// everything else becomes 0.  25 logic ops per 32 cells plus the 8 compares.
+CGL_HD void stable_update_sliced_rel(uint32_t (&p)[8], uint32_t surv, int max_rel)
 {
     uint32_t diff = 0;
-    for (int b = 0; b < 8; ++b) diff |= p[b] ^ (((stable_max >> b) & 1) ? 0xffffffffu : 0u);
+    for (int b = 0; b < 8; ++b) diff |= p[b] ^ (((max_rel >> b) & 1) ? 0xffffffffu : 0u);
     uint32_t c = surv & diff;                                  // cells that increment
     for (int b = 0; b < 8; ++b) {
         const uint32_t pb = p[b];
         const uint32_t n = pb ^ c;
         c &= pb;
-        p[b] = (surv & n) | (born & (((spawn >> b) & 1) ? 0xffffffffu : 0u));
+        p[b] = surv & n;
     }
 }
 

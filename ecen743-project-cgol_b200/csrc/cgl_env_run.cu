@@ -237,11 +237,14 @@ env_run_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, ui
 }
 
 // =========================================================================================
-// Bit-sliced variant for longer runs: the stability plane lives in REGISTERS as 8 bit planes per 32 cells
-// (cgl_bits.cuh), owned by the thread that owns the row; the rule is ~33 logic ops per 32 cells instead of
-// ~100 with bytes, the (born, surv) nibble plane and its barrier disappear (one barrier per step), and shared
-// memory only holds the two world bit planes.  The byte <-> bit-plane transposes on the way in and out cost
-// about four steps' worth of work, so cgl_env_run takes this kernel from max_steps >= 6.
+// Bit-sliced variant for longer runs.  Everything a thread owns stays in REGISTERS for the whole call: its
+// rows of the world (bit plane) and their stability as 8 bit planes per 32 cells (cgl_bits.cuh).  The rule
+// is ~33 logic ops per 32 cells instead of ~100 with bytes.  The only thing threads exchange per step are
+// the horizontal neighbour sums (s0, s1) of their rows, through a double-buffered shared-memory plane -- each
+// row's sums are computed once, by its owner -- and the barrier that publishes them also carries the
+// "did the previous step change anything" vote: one barrier per step.  The byte <-> bit-plane transposes on
+// the way in and out cost about five steps' worth of work, so cgl_env_run takes this kernel from
+// max_steps >= 4.
 // =========================================================================================
 template <int S>
 struct SlicedCfg {
@@ -252,7 +255,8 @@ struct SlicedCfg {
     static constexpr int EPC = (TPE >= 96) ? 1 : (128 / TPE);
     static constexpr int THREADS = TPE * EPC;
     static constexpr int RPB = S / TPE;
-    static constexpr int SMEM = EPC * (2 * WPE * 4) + EPC * 8;
+    // per env: two buffers x two planes (s0, s1) x WPE words
+    static constexpr int SMEM = EPC * (4 * WPE * 4) + EPC * 8;
 };
 
 template <int S>
@@ -266,29 +270,32 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int g = threadIdx.x / C::TPE;
     const int t = threadIdx.x % C::TPE;
-    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_dyn) + g * (2 * C::WPE);
-    uint32_t *nxt = cur + C::WPE;
-    int *red = reinterpret_cast<int *>(smem_dyn + C::EPC * (2 * C::WPE * 4)) + g * 2;
+    uint32_t *hbuf = reinterpret_cast<uint32_t *>(smem_dyn) + g * (4 * C::WPE);     // [buffer][plane][row][w]
+    int *red = reinterpret_cast<int *>(smem_dyn + C::EPC * (4 * C::WPE * 4)) + g * 2;
     const uint32_t e = blockIdx.x * C::EPC + g;
     const bool active = e < n_envs;
 
-    uint32_t pl[C::RPB][C::W][8];                   // this thread's rows: 8 bit planes per word
+    uint32_t cw[C::RPB][C::W];                      // this thread's rows of the world
+    uint32_t pl[C::RPB][C::W][8];                   // and their stability: 8 bit planes per word
     if (t == 0) { red[0] = 0; red[1] = 0; }
     if (active) {
-        const uint4 *wp = reinterpret_cast<const uint4 *>(world_in + (size_t)e * C::WPE);
-        for (int i = t; i < C::WPE / 4; i += C::TPE) reinterpret_cast<uint4 *>(cur)[i] = wp[i];
+        const uint32_t *wp = world_in + (size_t)e * C::WPE;
         const uint4 *sp = reinterpret_cast<const uint4 *>(stable + (size_t)e * C::SIZE);
 #pragma unroll
-        for (int j = 0; j < C::RPB; ++j)
+        for (int j = 0; j < C::RPB; ++j) {
+            lds_words<C::W>(wp + (t * C::RPB + j) * C::W, cw[j]);       // (plain loads: the helper is address-space agnostic)
 #pragma unroll
             for (int w = 0; w < C::W; ++w) {
                 const uint4 a = sp[((t * C::RPB + j) * S + w * 32) / 16];
                 const uint4 b = sp[((t * C::RPB + j) * S + w * 32) / 16 + 1];
                 const uint32_t by[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 bytes_to_planes32(by, pl[j][w]);
+                add_const_sliced(pl[j][w], -spawn);             // spawn-relative planes (cgl_bits.cuh)
             }
+        }
     }
     __syncthreads();
+    const int max_rel = (stable_max - spawn) & 0xff;
 
     auto env_vote = [&](bool p) -> bool {
         if constexpr (C::EPC == 1) return __syncthreads_or(p) != 0;
@@ -297,55 +304,74 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
         return r;
     };
 
-    uint32_t steps = 0;
-    bool done = !active || max_steps == 0;
-    while (!done) {
-        uint32_t changed = 0;
-        HSum hs[C::RPB + 2][C::W];
-        uint32_t cw[C::RPB + 2][C::W];
+    // rows above this thread's first row and below its last one (torus)
+    const int r_first = t * C::RPB, r_last = t * C::RPB + C::RPB - 1;
+    const int r_up = r_first == 0 ? S - 1 : r_first - 1;
+    const int r_dn = r_last == S - 1 ? 0 : r_last + 1;
+
+    uint32_t steps = 0, changed = 1u, buf = 0;
+    if (active) {
+        while (steps < max_steps) {
+            // horizontal sums of my rows; (s0, s1) go to the shared plane for the rows above and below
+            HSum hs[C::RPB][C::W];
+            uint32_t *h0 = hbuf + buf * (2 * C::WPE), *h1 = h0 + C::WPE;
 #pragma unroll
-        for (int j = 0; j < C::RPB + 2; ++j) {
-            int r = t * C::RPB + j - 1;
-            r = r < 0 ? S - 1 : (r >= S ? 0 : r);
-            lds_words<C::W>(cur + r * C::W, cw[j]);
+            for (int j = 0; j < C::RPB; ++j) {
+                uint32_t s0[C::W], s1[C::W];
 #pragma unroll
-            for (int w = 0; w < C::W; ++w)
-                hs[j][w] = hsum(west_plane(cw[j][(w + C::W - 1) % C::W], cw[j][w]), cw[j][w],
-                                east_plane(cw[j][w], cw[j][(w + 1) % C::W]));
-        }
-#pragma unroll
-        for (int j = 0; j < C::RPB; ++j) {
-            uint32_t nx[C::W];
-#pragma unroll
-            for (int w = 0; w < C::W; ++w) {
-                const uint32_t c = cw[j + 1][w];
-                const uint32_t n = life_rule(hs[j][w], hs[j + 1][w], hs[j + 2][w], c);
-                nx[w] = n;
-                changed |= n ^ c;
-                stable_update_sliced(pl[j][w], n & c, n & ~c, spawn, stable_max);
+                for (int w = 0; w < C::W; ++w) {
+                    hs[j][w] = hsum(west_plane(cw[j][(w + C::W - 1) % C::W], cw[j][w]), cw[j][w],
+                                    east_plane(cw[j][w], cw[j][(w + 1) % C::W]));
+                    s0[w] = hs[j][w].s0; s1[w] = hs[j][w].s1;
+                }
+                if (j == 0 || j == C::RPB - 1) {                // only edge rows are read by other threads
+                    sts_words<C::W>(h0 + (t * C::RPB + j) * C::W, s0);
+                    sts_words<C::W>(h1 + (t * C::RPB + j) * C::W, s1);
+                }
             }
-            sts_words<C::W>(nxt + (t * C::RPB + j) * C::W, nx);
+            // one barrier: publishes the sums and votes on whether the PREVIOUS step changed the world
+            const bool any_changed = env_vote(changed != 0);
+            if (stop_when_fixed && !any_changed) break;
+            uint32_t up0[C::W], up1[C::W], dn0[C::W], dn1[C::W];
+            lds_words<C::W>(h0 + r_up * C::W, up0);
+            lds_words<C::W>(h1 + r_up * C::W, up1);
+            lds_words<C::W>(h0 + r_dn * C::W, dn0);
+            lds_words<C::W>(h1 + r_dn * C::W, dn1);
+            changed = 0;
+#pragma unroll
+            for (int j = 0; j < C::RPB; ++j) {
+#pragma unroll
+                for (int w = 0; w < C::W; ++w) {
+                    const HSum up = {j == 0 ? up0[w] : hs[j > 0 ? j - 1 : 0][w].s0,
+                                     j == 0 ? up1[w] : hs[j > 0 ? j - 1 : 0][w].s1, 0, 0};
+                    const HSum dn = {j == C::RPB - 1 ? dn0[w] : hs[j < C::RPB - 1 ? j + 1 : 0][w].s0,
+                                     j == C::RPB - 1 ? dn1[w] : hs[j < C::RPB - 1 ? j + 1 : 0][w].s1, 0, 0};
+                    const uint32_t c = cw[j][w];
+                    const uint32_t n = life_rule(up, hs[j][w], dn, c);
+                    changed |= n ^ c;
+                    stable_update_sliced_rel(pl[j][w], n & c, max_rel);
+                    cw[j][w] = n;
+                }
+            }
+            ++steps;
+            buf ^= 1u;                              // the next step writes the other buffer: no reader is overtaken
         }
-        const bool any_changed = env_vote(changed != 0);     // the only barrier of the step
-        uint32_t *tmp = cur; cur = nxt; nxt = tmp;
-        ++steps;
-        done = steps >= max_steps || (stop_when_fixed && !any_changed);
     }
 
     int acc = 0;
     uint32_t pop = 0;
     if (active) {
-        uint4 *wo = reinterpret_cast<uint4 *>(world_out + (size_t)e * C::WPE);
-        for (int i = t; i < C::WPE / 4; i += C::TPE) {
-            const uint4 v = reinterpret_cast<const uint4 *>(cur)[i];
-            pop += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-            wo[i] = v;
-        }
+        uint32_t *wo = world_out + (size_t)e * C::WPE;
         uint4 *sp = reinterpret_cast<uint4 *>(stable + (size_t)e * C::SIZE);
 #pragma unroll
-        for (int j = 0; j < C::RPB; ++j)
+        for (int j = 0; j < C::RPB; ++j) {
+            sts_words<C::W>(wo + (t * C::RPB + j) * C::W, cw[j]);
 #pragma unroll
             for (int w = 0; w < C::W; ++w) {
+                pop += __popc(cw[j][w]);
+                add_const_sliced(pl[j][w], spawn);              // back to absolute values; dead cells are 0
+#pragma unroll
+                for (int b = 0; b < 8; ++b) pl[j][w][b] &= cw[j][w];
                 // reward = sum of int8 values = sum_b 2^b popc(plane b), the sign plane weighing -128
 #pragma unroll
                 for (int b = 0; b < 7; ++b) acc += __popc(pl[j][w][b]) << b;
@@ -355,6 +381,7 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
                 sp[((t * C::RPB + j) * S + w * 32) / 16] = make_uint4(by[0], by[1], by[2], by[3]);
                 sp[((t * C::RPB + j) * S + w * 32) / 16 + 1] = make_uint4(by[4], by[5], by[6], by[7]);
             }
+        }
     }
     acc = __reduce_add_sync(0xffffffffu, acc);
     pop = __reduce_add_sync(0xffffffffu, pop);
@@ -445,7 +472,8 @@ env_run_generic_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *st
     }
 }
 
-// CGL_RUN_IMPL=bytes | sliced forces one kernel (tests, tuning); default: sliced from 6 steps on.
+// CGL_RUN_IMPL=bytes | sliced forces one kernel (tests, tuning); default: sliced from 4 steps on
+// (measured on B200 at 4096 x 128^2: a launch costs ~50 us + 5.3 us per step sliced, ~25 us + 14 us per step bytes).
 static bool run_use_sliced(uint32_t max_steps)
 {
     static int forced = -1;
@@ -455,7 +483,7 @@ static bool run_use_sliced(uint32_t max_steps)
     }
     if (forced == 1) return false;
     if (forced == 2) return true;
-    return max_steps >= 6;
+    return max_steps >= 4;
 }
 
 template <int S>

@@ -86,7 +86,7 @@ def test_converge_batch_matches_oracle_env_by_env(cuda, side, n_envs, limit):
             assert len(seen) >= 3                               # the batch really had different trip counts
 
 
-@pytest.mark.parametrize("k", [3, 9])          # 3: the byte kernel, 9: the bit-sliced kernel (cgl_env_run.cu)
+@pytest.mark.parametrize("k", [3, 4, 9])       # 3: the byte kernel; 4, 9: the bit-sliced kernel (cgl_env_run.cu)
 @pytest.mark.parametrize("side", [32, 64, 96, 128, 160, 192, 224, 256, 5, 33, 100])
 def test_run_k_equals_k_steps(cuda, side, k):
     from cgl_b200.batched import BatchedSim

@@ -194,7 +194,11 @@ uint64_t twin_sliced_mismatches(const int8_t *cells, const uint8_t *tr, uint64_t
             if (tr[32 * g + j] == 0) surv |= 1u << j;
             if (tr[32 * g + j] == 1) born |= 1u << j;
         }
-        stable_update_sliced(p, surv, born, spawn, stable_max);
+        // as the kernel does: spawn-relative planes, the relative rule, back to absolute values masked by "alive"
+        add_const_sliced(p, -spawn);
+        stable_update_sliced_rel(p, surv, (stable_max - spawn) & 0xff);
+        add_const_sliced(p, spawn);
+        for (int b = 0; b < 8; ++b) p[b] &= surv | born;
         planes_to_bytes32(p, back);
         for (int j = 0; j < 32; ++j) {
             const int8_t want = stable_update1(cells[32 * g + j], tr[32 * g + j] == 0, tr[32 * g + j] != 2,
