@@ -455,7 +455,23 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
         for i in range(100, 100 + n):
             ref.toggle_state(acts[i]); ref.step(); acc_o += int(ref.reward())
         dt_o = time.perf_counter() - t0
+        # the reference's own bench loop (CGL/bench.py:39-40: plain steps, then Stability and Life are printed):
+        # the facade defers the plain steps and runs them as one on-chip launch when the result is asked for
+        # (a fresh env: the one above handed out a live shallow view, which switches the deferral off)
+        env2 = CGL.sim(side=side, seed=0, gpu=True, gpu_select=dev.index, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE)
+        ref.reset()
+        env2.step(); env2.step(); env2.step(); env2.step(); env2.reward()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            env2.step()
+        r_f, a_f = int(env2.reward()), int(env2.alive())
+        dt_b = time.perf_counter() - t0
+        for _ in range(n + 4):
+            ref.step()
+        del env2
+        plain_equal = (r_f, a_f) == (int(ref.reward()), int(ref.alive()))
         out["c1_single_64x64_loop"] = {"facade_env_steps_per_s": n / dt_f, "oracle_port_1core_env_steps_per_s": n / dt_o,
+                                       "facade_plain_step_loop_steps_per_s": n / dt_b, "plain_loop_equal": plain_equal,
                                        "reference_python_env_steps_per_s": 76.0,
                                        "reference_source": "BASELINE.md section 2 (measured in the survey container)",
                                        "rewards_equal": acc == acc_o}
@@ -473,6 +489,8 @@ def run_extras(torch, dev, rank, world, barrier, max_over_ranks, peak):
             def run(_i):
                 native.check(lib.cgl_life_run(native.dptr(a), native.dptr(b), n, n, 1, g, k, native.ctypes.byref(res),
                                               native.current_stream()))
+            if k > 1:        # set-up: let the library time its strip lengths for this shape (RowBandLife does the same)
+                native.check(lib.cgl_life_tune(native.dptr(a), native.dptr(b), n, n, 1, k, native.current_stream()))
             run(0)
             dt = time_steps(torch, run, 2, barrier) / 2
             sweep[f"k{k}"] = {"gcups": n * n * g / dt / 1e9, "us_per_gen": dt / g * 1e6,

@@ -21,7 +21,10 @@ Deliberate deviations (all documented in DESIGN.md section 2):
     (reads see live state, aliasing `state is n_state` holds, CGL/main.py:60,70); writes INTO a
     shallow view do not reach the device -- use toggle_state / update_state / load;
   * a single-index toggle_state is applied lazily: it is fused into the next step() launch, or applied
-    by the next other call into the env; a shallow view shows it from that call on.
+    by the next other call into the env; a shallow view shows it from that call on;
+  * plain step() calls are deferred while no shallow view is live and executed together (one on-chip
+    launch for the whole run of steps) when the state is next observed or changed -- same results, and
+    the reference's `for _ in range(iters): env.step()` loop costs one launch.
 """
 from __future__ import annotations
 
@@ -172,15 +175,29 @@ class sim:
         self._m_reward_t = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._m_action, self._m_reward = self._m_action_t.numpy(), self._m_reward_t.numpy()
         self._pending = None                                # scalar toggle deferred into the next step()
+        self._lazy_steps = 0                                # plain steps not yet executed (see step())
         self._reward_valid = False                          # _m_reward holds reward() of the current state
 
     def _flush(self):
-        """Apply a deferred scalar toggle now (anything that observes the state between toggle_state and
-        step must see it)."""
+        """Bring the device state up to date with everything the caller has asked for so far: run the plain
+        steps that were deferred (see step()), then apply a deferred scalar toggle (anything that observes the
+        state between toggle_state and step must see it)."""
+        self._run_lazy()
         if self._pending is not None:
             a, self._pending = self._pending, None
             self._b.toggle(self._torch.tensor([[a]], dtype=self._torch.int32, device=self._dev))
             self._reward_valid = False
+            self._changed()
+
+    def _run_lazy(self):
+        n, self._lazy_steps = self._lazy_steps, 0
+        if n == 1:
+            self._step_now()
+        elif n > 1:                 # the whole run of plain steps is ONE launch with the env resident on chip
+            with self._torch.cuda.device(self._dev):
+                _, rew, _ = self._b.run(n)
+                self._m_reward_t.copy_(rew, non_blocking=True)
+            self._reward_valid = True
             self._changed()
 
     def _changed(self, world=True, stable=True):
@@ -234,10 +251,24 @@ class sim:
 
     # ------------------------------------------------------------------------------ simulator
     def step(self, forceCPU=False):
-        """One generation + stability update (CGL/CGL.py:247-252; kernel :147-181)."""
+        """One generation + stability update (CGL/CGL.py:247-252; kernel :147-181).
+
+        A plain step (no toggle pending) while nobody holds a live shallow view is only COUNTED here and
+        executed when the state is next observed or changed (reward, alive, get_*, toggle_state, ...): a loop
+        like the reference's `for _ in range(iters): env.step()` (CGL/bench.py:39-40) becomes one launch of
+        `cgl_env_run(iters)` with the env resident on chip.  Results are bit-identical either way."""
         if forceCPU:
             raise RuntimeError("forceCPU is not available in the B200 build (no CPU step); use the reference for that")
         self.count += 1
+        if self._pending is None and not (self._world_live or self._stable_live) and self._can_defer:
+            self._lazy_steps += 1
+            self._reward_valid = False
+            self._world_fresh = self._stable_fresh = False
+            return
+        self._run_lazy()
+        self._step_now()
+
+    def _step_now(self):
         # toggle (if one is pending) + generation + stability + reward in one launch; the action word is
         # read from, and the reward written to, pinned host memory
         actions_ptr = 0
@@ -253,6 +284,10 @@ class sim:
                 self._m_reward_t.copy_(self._b._reward, non_blocking=True)
         self._reward_valid = True
         self._changed()
+
+    @property
+    def _can_defer(self):
+        return self._b.fused or self.side <= 273            # sides cgl_env_run can keep on chip
 
     # ---- extensions (not in CGL/CGL.py): the reference's own loops around step(), run on the device ----
     def run(self, iters, until_fixed=False):
@@ -299,6 +334,7 @@ class sim:
     def reset(self):
         """Back to the initial state; `count` is not reset (CGL/CGL.py:264-266)."""
         self._pending = None
+        self._lazy_steps = 0                                # whatever was still owed is overwritten by the reset
         self._reward_valid = False
         self._b.reset()
         self._changed()
@@ -411,6 +447,7 @@ class sim:
             raise ValueError(f"newState/newstable must have side*side = {side * side} cells")
         from cgl_b200.batched import BatchedSim
         self._pending = None
+        self._lazy_steps = 0
         self._reward_valid = False
         self.stableStabilityFactor = stableStabilityFactor
         self.spawnStabilityFactor = spawnStabilityFactor

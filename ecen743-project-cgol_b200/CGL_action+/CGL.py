@@ -80,6 +80,7 @@ class sim(_base.sim):
         """A new random world from `seed`, stability re-initialised (CGL_action+/CGL.py:282-287); count,
         initState and initStable are left alone like in the fork."""
         self._pending = None
+        self._lazy_steps = 0
         self._reward_valid = False
         np.random.seed(seed)
         cells = np.random.randint(2, size=self.size, dtype=np.uint8)
