@@ -258,6 +258,28 @@ CGL_HD void stable_update_sliced_rel(uint32_t (&p)[8], uint32_t surv, int max_re
     }
 }
 
+// The CGL_action+ fork's decay rule (CGL_DEAD_DECAY) on spawn-relative bit planes.  Here dead cells DO carry a
+// value (they fall by one per step down to EMPTY_MIN), so all cells are kept relative to SPAWN: survivors
+// add 1 unless u == max_rel, dead cells subtract 1 unless u == min_rel (= EMPTY_MIN - SPAWN mod 256), born
+// cells become 0.  One ripple pass adds the per-cell operand D (bit 0 = inc | dec, bits 1..7 = dec).
+CGL_HD void stable_update_sliced_decay(uint32_t (&p)[8], uint32_t surv, uint32_t born, int max_rel, int min_rel)
+{
+    uint32_t dmax = 0, dmin = 0;
+    for (int b = 0; b < 8; ++b) {
+        dmax |= p[b] ^ (((max_rel >> b) & 1) ? 0xffffffffu : 0u);
+        dmin |= p[b] ^ (((min_rel >> b) & 1) ? 0xffffffffu : 0u);
+    }
+    const uint32_t dec = ~(surv | born) & dmin;                // dead cells above the floor
+    const uint32_t d0 = (surv & dmax) | dec;
+    const uint32_t keep = ~born;
+    uint32_t c = 0;
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t pb = p[b], db = b == 0 ? d0 : dec;
+        p[b] = (pb ^ db ^ c) & keep;
+        c = (pb & db) | (c & (pb | db));
+    }
+}
+
 // Expand a 4-bit nibble to 4 byte masks (bit i -> byte i = 0xFF).
 CGL_HD uint32_t nibble_to_bytemask(uint32_t nib)
 {

@@ -259,10 +259,12 @@ struct SlicedCfg {
     static constexpr int SMEM = EPC * (4 * WPE * 4) + EPC * 8;
 };
 
-template <int S>
+// DECAY = false: the base env (dead cells are 0; "don't care" planes).  DECAY = true: the CGL_action+ fork's
+// CUDA-kernel rule (dead cells fall by one per step to EMPTY_MIN), all cells carried spawn-relative.
+template <int S, bool DECAY>
 __global__ void __launch_bounds__(SlicedCfg<S>::THREADS)
 env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t n_envs,
-                      uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max,
+                      uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max, int empty_min,
                       int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out,
                       uint32_t *__restrict__ alive_out)
 {
@@ -295,7 +297,7 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
         }
     }
     __syncthreads();
-    const int max_rel = (stable_max - spawn) & 0xff;
+    const int max_rel = (stable_max - spawn) & 0xff, min_rel = (empty_min - spawn) & 0xff;
 
     auto env_vote = [&](bool p) -> bool {
         if constexpr (C::EPC == 1) return __syncthreads_or(p) != 0;
@@ -349,7 +351,8 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
                     const uint32_t c = cw[j][w];
                     const uint32_t n = life_rule(up, hs[j][w], dn, c);
                     changed |= n ^ c;
-                    stable_update_sliced_rel(pl[j][w], n & c, max_rel);
+                    if constexpr (DECAY) stable_update_sliced_decay(pl[j][w], n & c, n & ~c, max_rel, min_rel);
+                    else stable_update_sliced_rel(pl[j][w], n & c, max_rel);
                     cw[j][w] = n;
                 }
             }
@@ -370,8 +373,10 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
             for (int w = 0; w < C::W; ++w) {
                 pop += __popc(cw[j][w]);
                 add_const_sliced(pl[j][w], spawn);              // back to absolute values; dead cells are 0
+                if constexpr (!DECAY) {
 #pragma unroll
-                for (int b = 0; b < 8; ++b) pl[j][w][b] &= cw[j][w];
+                    for (int b = 0; b < 8; ++b) pl[j][w][b] &= cw[j][w];
+                }
                 // reward = sum of int8 values = sum_b 2^b popc(plane b), the sign plane weighing -128
 #pragma unroll
                 for (int b = 0; b < 7; ++b) acc += __popc(pl[j][w][b]) << b;
@@ -496,10 +501,14 @@ static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, u
     if (once.first())
         CGL_CUDA(cudaFuncSetAttribute(env_run_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
-    if (rule == CGL_DEAD_ZERO && run_use_sliced(max_steps)) {      // the bit-sliced kernel knows the base rule only
+    if (rule != CGL_DEAD_SAT && run_use_sliced(max_steps)) {       // (the saturating rule stays on the byte kernel)
         using D = SlicedCfg<S>;
-        env_run_sliced_kernel<S><<<grid, D::THREADS, D::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps,
-                                                                   stop, spawn, stable_max, steps, reward, alive);
+        if (rule == CGL_DEAD_DECAY)
+            env_run_sliced_kernel<S, true><<<grid, D::THREADS, D::SMEM, st>>>(
+                win, wout, stable, (uint32_t)n_envs, max_steps, stop, spawn, stable_max, empty_min, steps, reward, alive);
+        else
+            env_run_sliced_kernel<S, false><<<grid, D::THREADS, D::SMEM, st>>>(
+                win, wout, stable, (uint32_t)n_envs, max_steps, stop, spawn, stable_max, empty_min, steps, reward, alive);
     } else {
         env_run_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, stop,
                                                             rep4(spawn), rep4(stable_max), steps, reward, alive, rule,

@@ -162,3 +162,22 @@ def test_bit_sliced_stability_equals_scalar_rule(twin, spawn, smax):
             tr[g, pos] = t
     cells[768:800] = np.int8(smax)                      # whole groups at the ceiling
     assert twin.twin_sliced_mismatches(P(cells), P(tr), groups, spawn, smax) == 0
+
+
+@pytest.mark.parametrize("spawn,smax,emin", [(-2, 2, -6), (-128, 127, -128), (5, 127, -3), (-2, 3, -128), (0, 0, 0), (7, -3, 100)])
+def test_bit_sliced_decay_rule_equals_scalar_rule(twin, spawn, smax, emin):
+    twin.twin_sliced_decay_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int]
+    twin.twin_sliced_decay_mismatches.restype = ctypes.c_uint64
+    rs = np.random.RandomState(abs(spawn) + abs(emin))
+    groups = 256 * 3 + 400
+    cells = rs.randint(-128, 128, size=(groups, 32)).astype(np.int8)
+    tr = rs.randint(0, 3, size=(groups, 32)).astype(np.uint8)
+    for v in range(256):
+        for t in range(3):
+            pos = rs.randint(32)
+            cells[v * 3 + t, pos] = np.int8(v - 128)
+            tr[v * 3 + t, pos] = t
+    cells[768:790] = np.int8(emin)                      # whole groups on the floor / at the ceiling
+    cells[790:812] = np.int8(smax)
+    assert twin.twin_sliced_decay_mismatches(P(cells), P(tr), groups, spawn, smax, emin) == 0

@@ -262,3 +262,28 @@ def test_fork_facade_run(fork):
     assert env.run(c["limit"] + 1, until_fixed=True) == c["steps"]
     assert int(env.stability()) == c["stability"] and int(env.alive()) == c["alive"]
     assert env.breakdown_stable().tolist() == c["breakdown"]
+
+
+@pytest.mark.parametrize("side,n_envs,limit", [(32, 20, 90), (64, 9, 40), (128, 4, 15), (96, 3, 12), (10, 12, 80)])
+def test_fork_decay_run_until_fixed_vs_oracle(cuda, side, n_envs, limit):
+    """The fork's default (CUDA-kernel) rule through the on-chip run kernels (bit-sliced for fused sides), with
+    envs that stop after different numbers of steps."""
+    from cgl_b200.batched import BatchedSim
+    size = side * side
+    rng = np.random.RandomState(side)
+    dens = rng.choice([0.03, 0.08, 0.2, 0.5], size=n_envs)
+    cells = (rng.random_sample((n_envs, size)) < dens[:, None]).astype(np.uint8)
+    cells[0] = 0
+    spawn, smax, empty, emin = -2, 3, -1, -9
+    env = BatchedSim(n_envs, side, states=cells, spawnStabilityFactor=spawn, stableStabilityFactor=smax,
+                     dead_rule="decay", empty=empty, empty_min=emin, masked_toggle=True)
+    obs, rew, steps = env.run(limit, until_fixed=True, want_alive=True)
+    w_g, o_g, r_g, s_g = env.get_state().cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), steps.cpu().numpy()
+    for e in range(n_envs):
+        w = cells[e].copy()
+        s = oracle.initial_stable_fork(w, spawn, empty)
+        n = oracle.run_rule(w, s, side, spawn, smax, limit, oracle.DEAD_DECAY, empty, emin, until_fixed=True)
+        assert s_g[e] == n, (e, s_g[e], n)
+        assert np.array_equal(w_g[e], w) and np.array_equal(o_g[e], s), e
+        assert r_g[e] == int(oracle.reward(s))
+    assert s_g[0] == 1

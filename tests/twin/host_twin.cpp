@@ -209,4 +209,31 @@ uint64_t twin_sliced_mismatches(const int8_t *cells, const uint8_t *tr, uint64_t
     return bad;
 }
 
+// The fork's decay rule on spawn-relative bit planes against the scalar rule (tr: 0 survive, 1 born, 2 dead).
+uint64_t twin_sliced_decay_mismatches(const int8_t *cells, const uint8_t *tr, uint64_t n_groups, int spawn,
+                                      int stable_max, int empty_min)
+{
+    uint64_t bad = 0;
+    for (uint64_t g = 0; g < n_groups; ++g) {
+        uint32_t w[8], p[8], back[8], surv = 0, born = 0;
+        memcpy(w, cells + 32 * g, 32);
+        bytes_to_planes32(w, p);
+        for (int j = 0; j < 32; ++j) {
+            if (tr[32 * g + j] == 0) surv |= 1u << j;
+            if (tr[32 * g + j] == 1) born |= 1u << j;
+        }
+        add_const_sliced(p, -spawn);
+        stable_update_sliced_decay(p, surv, born, (stable_max - spawn) & 0xff, (empty_min - spawn) & 0xff);
+        add_const_sliced(p, spawn);
+        planes_to_bytes32(p, back);
+        for (int j = 0; j < 32; ++j) {
+            const int8_t want = stable_update1_rule(CGL_DEAD_DECAY, cells[32 * g + j], tr[32 * g + j] == 0,
+                                                    tr[32 * g + j] != 2, (int8_t)spawn, (int8_t)stable_max, 0,
+                                                    (int8_t)empty_min);
+            bad += ((const int8_t *)back)[j] != want;
+        }
+    }
+    return bad;
+}
+
 }  // extern "C"
