@@ -12,6 +12,12 @@ toggle_state (:322-328) -> step (:247-252, kernel :147-181) -> reward (:255-256)
 Sharding by env index (multi-GPU, no communication): `BatchedSim.shard(...)` gives rank r the
 envs [r*B/G, (r+1)*B/G); env e is always seeded `seed + e` with its GLOBAL index, so results
 do not depend on the number of GPUs.
+
+Beyond the single step:
+  step(obs_out=, reward_out=)   the new observation goes straight into a caller buffer (replay ring, dqn.py)
+  run(k, until_fixed=)          k plain steps / run-until-fixed in one launch, env resident on chip
+  dead_rule=, empty=, empty_min=, masked_toggle=   the CGL_action+ fork's env
+  breakdown_stable / breakdown_state, block_action, save_checkpoint / load_checkpoint, step_host(sync=False)
 """
 from __future__ import annotations
 
