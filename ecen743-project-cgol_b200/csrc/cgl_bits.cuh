@@ -150,11 +150,32 @@ CGL_HD uint32_t dead_value4(int rule, uint32_t s, uint32_t min4, uint32_t empty4
     return 0u;
 }
 
+// The decay rule for 4 cells as ONE bytewise addition: every byte gets a delta of +1 (survivor below MAX), -1 = 0xFF
+// (dead cell above MIN) or 0, then born cells are overwritten with SPAWN.  The two "byte != constant" tests
+// leave their answer in bit 7 of each byte, already masked with the cell class; bit 7 -> delta runs on the FMA
+// pipe (IMAD.HI / IMAD), which the integer-pipe-bound kernel has to spare.
+CGL_HD uint32_t stable_update4_decay(uint32_t s, uint32_t surv_mask, uint32_t born_mask, uint32_t spawn4,
+                                     uint32_t max4, uint32_t min4)
+{
+    const uint32_t H = 0x80808080u, L = 0x7f7f7f7fu;
+    const uint32_t xa = s ^ max4, xb = s ^ min4;
+    const uint32_t inc7 = (((xa & L) + L) | xa) & (surv_mask & H);                  // bit 7: survivor and s != MAX
+    const uint32_t dec7 = (((xb & L) + L) | xb) & (~(surv_mask | born_mask) & H);   // bit 7: dead and s != MIN
+#if defined(__CUDA_ARCH__)
+    const uint32_t d = __umulhi(dec7, 1u << 25) * 255u + __umulhi(inc7, 1u << 25);  // bytes: 0xFF / 0x01 / 0x00
+#else
+    const uint32_t d = (dec7 >> 7) * 255u + (inc7 >> 7);
+#endif
+    const uint32_t sum = ((s & L) + (d & L)) ^ ((s ^ d) & H);                       // bytewise s + d, wraps like int8
+    return (sum & ~born_mask) | (spawn4 & born_mask);
+}
+
 // stable' for 4 cells with a dead-cell rule: surv_mask / born_mask are byte masks (0xFF) of the cells that
 // stayed alive / were born.
 CGL_HD uint32_t stable_update4_rule(int rule, uint32_t s, uint32_t surv_mask, uint32_t born_mask, uint32_t spawn4,
                                     uint32_t max4, uint32_t min4, uint32_t empty4)
 {
+    if (rule == CGL_DEAD_DECAY) return stable_update4_decay(s, surv_mask, born_mask, spawn4, max4, min4);
     const uint32_t live = (inc_unless_max4(s, max4) & surv_mask) | (spawn4 & born_mask);
     return live | (dead_value4(rule, s, min4, empty4) & ~(surv_mask | born_mask));
 }

@@ -90,19 +90,21 @@ struct RuleArgs { int rule, empty, empty_min, masked; };
 // IO = false: the stability plane is updated in place.  IO = true: it is read from `stable` and the
 // new values go to `stable_out` (another buffer of the same shape) -- the replay ring of the batched
 // DQN loop hands the env its next observation slot, so "adding to the replay buffer" costs no copy.
-// EXT = true: the CGL_action+ fork's variants (cgl_bits.cuh): `rule` for cells that are dead after the step
-// (decay / saturate instead of zero; min4 / empty4 = EMPTY_MIN / EMPTY replicated) and `masked` toggles
-// (a cell toggled to dead gets 0, not SPAWN: CGL_action+/CGL.py:382-384).  EXT = false is the base env and
-// compiles to exactly the code it had before these parameters existed.
-template <int S, bool IO, bool EXT>
+// RULE >= 0: the CGL_action+ fork's variants (cgl_bits.cuh): the rule for cells that are dead after the step
+// (CGL_DEAD_ZERO / DECAY / SAT; min4 / empty4 = EMPTY_MIN / EMPTY replicated) and `masked` toggles (a cell
+// toggled to dead gets 0, not SPAWN: CGL_action+/CGL.py:382-384).  RULE = -1 is the base env and compiles to
+// exactly the code it had before these parameters existed.  The rule is a template parameter on purpose: as a
+// run-time switch inside the unrolled stability loop it tripled the branch count and cost ~15 %.
+template <int S, bool IO, int RULE>
 __global__ void __launch_bounds__(EnvCfg<S>::THREADS)
 env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out,
                       int8_t *stable, int8_t *stable_out, uint32_t n_envs,
                       const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
                       int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish,
-                      int rule, uint32_t min4, uint32_t empty4, int masked)
+                      uint32_t min4, uint32_t empty4, int masked)
 {
+    constexpr bool EXT = RULE >= 0;
     using C = EnvCfg<S>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     // Mask tables, one copy per lane so that a lookup never bank-conflicts:
@@ -287,7 +289,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                     const uint32_t surv_mask = lds_u32(__byte_perm(sv, lane_s, 0x5504 + 16 * k));
                     if constexpr (EXT) {
                         const uint32_t born_mask = lds_u32(__byte_perm(bn, lane_s, 0x5504 + 16 * k));
-                        s[k] = stable_update4_rule(rule, s[k], surv_mask, born_mask, spawn4, max4, min4, empty4);
+                        s[k] = stable_update4_rule(RULE, s[k], surv_mask, born_mask, spawn4, max4, min4, empty4);
                     } else {
                         const uint32_t born_spawn = lds_u32(__byte_perm(bn, lane_b, 0x5504 + 16 * k));
                         s[k] = stable_update4(s[k], surv_mask, born_spawn, max4);
@@ -345,11 +347,15 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
         pad = v ? atoi(v) : 0;
     }
     if (once.first()) {
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false, false>,
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, false, -1>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, false>,
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, -1>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
-        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, true>,
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, CGL_DEAD_ZERO>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, CGL_DEAD_DECAY>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
+        CGL_CUDA(cudaFuncSetAttribute(env_step_fused_kernel<S, true, CGL_DEAD_SAT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad));
     }
     cudaLaunchConfig_t cfg = {};
@@ -362,19 +368,26 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (ext != nullptr)                 // fork variants: one instantiation (separate in/out planes; they may alias)
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, true>, win, wout, stable,
-                                    stable_out != nullptr ? stable_out : stable, (uint32_t)n_envs, actions,
-                                    rep4(spawn), rep4(stable_max), reward, alive, err, epoch, want, publish,
-                                    ext->rule, rep4(ext->empty_min), rep4(ext->empty), ext->masked));
-    else if (stable_out != nullptr && stable_out != stable)
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, false>, win, wout, stable, stable_out,
-                                    (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
-                                    epoch, want, publish, 0, 0u, 0u, 0));
-    else
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false, false>, win, wout, stable, stable,
-                                    (uint32_t)n_envs, actions, rep4(spawn), rep4(stable_max), reward, alive, err,
-                                    epoch, want, publish, 0, 0u, 0u, 0));
+    const uint32_t n32 = (uint32_t)n_envs, sp4 = rep4(spawn), mx4 = rep4(stable_max);
+    if (ext != nullptr) {               // fork variants: separate in/out planes (they may alias), one kernel per rule
+        int8_t *so = stable_out != nullptr ? stable_out : stable;
+        const uint32_t mn4 = rep4(ext->empty_min), em4 = rep4(ext->empty);
+        if (ext->rule == CGL_DEAD_DECAY)
+            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_DECAY>, win, wout, stable, so, n32,
+                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
+        else if (ext->rule == CGL_DEAD_SAT)
+            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_SAT>, win, wout, stable, so, n32,
+                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
+        else
+            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_ZERO>, win, wout, stable, so, n32,
+                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
+    } else if (stable_out != nullptr && stable_out != stable) {
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, -1>, win, wout, stable, stable_out, n32, actions,
+                                    sp4, mx4, reward, alive, err, epoch, want, publish, 0u, 0u, 0));
+    } else {
+        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false, -1>, win, wout, stable, stable, n32, actions,
+                                    sp4, mx4, reward, alive, err, epoch, want, publish, 0u, 0u, 0));
+    }
     return 0;
 }
 
