@@ -236,4 +236,68 @@ uint64_t twin_sliced_decay_mismatches(const int8_t *cells, const uint8_t *tr, ui
     return bad;
 }
 
+// mirrors env_run_sliced_kernel<S, DECAY> (csrc/cgl_env_run.cu) for ONE env, side % 32 == 0: rows of the world
+// and spawn-relative bit planes per row owner, horizontal sums (s0, s1) published once per row and step, the
+// vote on the PREVIOUS step's change taken at the same point as the kernel's barrier.  Returns the steps executed.
+int twin_env_run_sliced(uint32_t *world, int8_t *stable, uint32_t side, uint32_t max_steps, int stop_when_fixed,
+                        int spawn, int stable_max, int decay, int empty_min)
+{
+    if (side % 32) return -1;
+    const int S = (int)side, W = S / 32;
+    std::vector<uint32_t> cw(world, world + S * W), pl((size_t)S * W * 8), h0(S * W), h1(S * W);
+    const uint32_t *sb = reinterpret_cast<const uint32_t *>(stable);
+    for (int r = 0; r < S; ++r)
+        for (int w = 0; w < W; ++w) {
+            uint32_t by[8], p[8];
+            memcpy(by, sb + ((size_t)r * S + w * 32) / 4, 32);
+            bytes_to_planes32(by, p);
+            add_const_sliced(p, -spawn);
+            memcpy(&pl[((size_t)r * W + w) * 8], p, 32);
+        }
+    const int max_rel = (stable_max - spawn) & 0xff, min_rel = (empty_min - spawn) & 0xff;
+    uint32_t steps = 0, changed = 1;
+    while (steps < max_steps) {
+        std::vector<HSum> hs(S * W);
+        for (int r = 0; r < S; ++r)
+            for (int w = 0; w < W; ++w) {
+                const uint32_t c = cw[r * W + w];
+                hs[r * W + w] = hsum(west_plane(cw[r * W + (w + W - 1) % W], c), c, east_plane(c, cw[r * W + (w + 1) % W]));
+                h0[r * W + w] = hs[r * W + w].s0;
+                h1[r * W + w] = hs[r * W + w].s1;
+            }
+        if (stop_when_fixed && !changed) break;                 // the vote rides on the barrier that publishes the sums
+        changed = 0;
+        std::vector<uint32_t> nw(S * W);
+        for (int r = 0; r < S; ++r)
+            for (int w = 0; w < W; ++w) {
+                const int ru = (r == 0 ? S - 1 : r - 1), rd = (r == S - 1 ? 0 : r + 1);
+                const HSum up = {h0[ru * W + w], h1[ru * W + w], 0, 0}, dn = {h0[rd * W + w], h1[rd * W + w], 0, 0};
+                const uint32_t c = cw[r * W + w];
+                const uint32_t n = life_rule(up, hs[r * W + w], dn, c);
+                changed |= n ^ c;
+                uint32_t p[8];
+                memcpy(p, &pl[((size_t)r * W + w) * 8], 32);
+                if (decay) stable_update_sliced_decay(p, n & c, n & ~c, max_rel, min_rel);
+                else stable_update_sliced_rel(p, n & c, max_rel);
+                memcpy(&pl[((size_t)r * W + w) * 8], p, 32);
+                nw[r * W + w] = n;
+            }
+        cw = nw;
+        ++steps;
+    }
+    uint32_t *so = reinterpret_cast<uint32_t *>(stable);
+    for (int r = 0; r < S; ++r)
+        for (int w = 0; w < W; ++w) {
+            uint32_t p[8], by[8];
+            memcpy(p, &pl[((size_t)r * W + w) * 8], 32);
+            add_const_sliced(p, spawn);
+            if (!decay)
+                for (int b = 0; b < 8; ++b) p[b] &= cw[r * W + w];
+            planes_to_bytes32(p, by);
+            memcpy(so + ((size_t)r * S + w * 32) / 4, by, 32);
+            world[r * W + w] = cw[r * W + w];
+        }
+    return (int)steps;
+}
+
 }  // extern "C"
