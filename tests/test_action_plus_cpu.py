@@ -134,3 +134,60 @@ def test_oracle_run_rule_matches_the_forks_loops(c):
     assert hashlib.sha256(world.tobytes()).hexdigest() == c["world_sha"]
     assert hashlib.sha256(stable.tobytes()).hexdigest() == c["stable_sha"]
     assert oracle.breakdown(stable).tolist() == c["breakdown"]
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(FORK_TRACES) if FORK_TRACES[n].side % 32 == 0])
+def test_twin_fused_rule_path_replays_fork_trace(twin, name):
+    """The fused kernel's logic with the fork's variants (nibble tables -> 4-cells-per-word rule, masked toggle
+    applied inside the step), restated on the host from the same header."""
+    twin.twin_env_step_fused_rule.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p] + \
+        [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
+    twin.twin_env_step_fused_rule.restype = ctypes.c_int
+    tr = FORK_TRACES[name]
+    side, W = tr.side, tr.side // 32
+    w = np.zeros(side * W, np.uint32)
+    cells0 = np.ascontiguousarray(tr.worlds[0])          # keep the buffer alive across the ctypes call
+    twin.twin_pack(P(cells0), P(w), 1, side, side)
+    s = tr.stables[0].copy()
+    for t in range(tr.T):
+        a = tr.action(t)
+        assert a is None or isinstance(a, int)
+        acts = np.array([tr.size if a is None else a], np.int32)
+        nxt, rew, alv = np.zeros_like(w), np.zeros(1, np.int32), np.zeros(1, np.uint32)
+        rc = twin.twin_env_step_fused_rule(P(w), P(nxt), P(s), 1, side, P(acts), tr.spawn, tr.stable_max, oracle.DEAD_SAT,
+                                           tr.empty, tr.empty_min, 1, P(rew), P(alv))
+        assert rc == 0
+        w = nxt
+        cells = np.zeros(side * side, np.uint8)
+        twin.twin_unpack(P(w), P(cells), 1, side, side)
+        assert np.array_equal(cells, tr.worlds[t + 1]) and np.array_equal(s, tr.stables[t + 1]), (name, t)
+        assert int(rew[0]) == tr.stability[t + 1] and int(alv[0]) == tr.alives[t + 1]
+
+
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_twin_fused_rule_path_random_vs_oracle(twin, rule):
+    twin.twin_env_step_fused_rule.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p] + \
+        [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
+    twin.twin_env_step_fused_rule.restype = ctypes.c_int
+    rs = np.random.RandomState(rule)
+    for side in (32, 64, 96):
+        size, W = side * side, side // 32
+        spawn, smax, empty, emin = -2, 3, -1, -7
+        world = rs.randint(2, size=size).astype(np.uint8)
+        stable = rs.randint(-128, 128, size=size).astype(np.int8)
+        w = np.zeros(side * W, np.uint32)
+        twin.twin_pack(P(world), P(w), 1, side, side)
+        s = stable.copy()
+        for t in range(6):
+            a = int(rs.randint(size + 1))
+            acts = np.array([a], np.int32)
+            nxt, rew, alv = np.zeros_like(w), np.zeros(1, np.int32), np.zeros(1, np.uint32)
+            assert twin.twin_env_step_fused_rule(P(w), P(nxt), P(s), 1, side, P(acts), spawn, smax, rule, empty, emin, 1,
+                                                 P(rew), P(alv)) == 0
+            w = nxt
+            oracle.toggle_masked(world, stable, a, spawn)
+            oracle.step_rule(world, stable, side, spawn, smax, rule, empty, emin)
+            cells = np.zeros(size, np.uint8)
+            twin.twin_unpack(P(w), P(cells), 1, side, side)
+            assert np.array_equal(cells, world) and np.array_equal(s, stable), (rule, side, t)
+            assert int(rew[0]) == int(oracle.reward(stable))

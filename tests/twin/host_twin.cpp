@@ -300,4 +300,63 @@ int twin_env_run_sliced(uint32_t *world, int8_t *stable, uint32_t side, uint32_t
     return (int)steps;
 }
 
+// mirrors env_step_fused_kernel<S, IO, RULE >= 0>: the CGL_action+ variants (dead-cell rule, masked toggle)
+int twin_env_step_fused_rule(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint64_t n_envs,
+                             uint32_t side, const int32_t *actions, int spawn, int stable_max, int rule, int empty,
+                             int empty_min, int masked, int32_t *reward_out, uint32_t *alive_out)
+{
+    if (side % 32) return -1;
+    const int S = (int)side, W = S / 32, WPE = S * W, SIZE = S * S, NCHUNK = SIZE / 16;
+    const uint32_t spawn4 = rep4(spawn), max4 = rep4(stable_max), min4 = rep4(empty_min), empty4 = rep4(empty);
+    uint32_t table[16][2];                       // [nibble][0] = byte mask, [1] = mask & SPAWN
+    for (uint32_t i = 0; i < 16; ++i) { table[i][0] = nibble_to_bytemask(i); table[i][1] = table[i][0] & spawn4; }
+    std::vector<uint32_t> cur(WPE), mix(2 * WPE);
+    int err = 0;
+    for (uint64_t e = 0; e < n_envs; ++e) {
+        int act = -1;
+        if (actions) {
+            int a = actions[e];
+            if (a >= 0 && a < SIZE) act = a;
+            else if (a != SIZE) err = 1;
+        }
+        memcpy(cur.data(), world_in + e * WPE, WPE * 4);
+        if (act >= 0) cur[act >> 5] ^= 1u << (act & 31);
+        uint32_t pop = 0;
+        for (int i = 0; i < WPE; ++i) {
+            const int r = i / W, w = i % W;
+            const int ru = (r == 0 ? S - 1 : r - 1) * W, rc = r * W, rd = (r == S - 1 ? 0 : r + 1) * W;
+            const int wl = (w == 0 ? W - 1 : w - 1), wr = (w == W - 1 ? 0 : w + 1);
+            const uint32_t a = cur[ru + w], c = cur[rc + w], b = cur[rd + w];
+            const HSum ha = hsum(west_plane(cur[ru + wl], a), a, east_plane(a, cur[ru + wr]));
+            const HSum hc = hsum(west_plane(cur[rc + wl], c), c, east_plane(c, cur[rc + wr]));
+            const HSum hb = hsum(west_plane(cur[rd + wl], b), b, east_plane(b, cur[rd + wr]));
+            const uint32_t nxt = life_rule(ha, hc, hb, c);
+            world_out[e * WPE + i] = nxt;
+            pop += __builtin_popcount(nxt);
+            mix_nibbles(nxt & ~c, nxt & c, mix[2 * i], mix[2 * i + 1]);
+        }
+        uint32_t *sp = reinterpret_cast<uint32_t *>(stable + e * SIZE);
+        int32_t acc = 0;
+        for (int q = 0; q < NCHUNK; ++q) {
+            uint32_t s[4] = {sp[4 * q], sp[4 * q + 1], sp[4 * q + 2], sp[4 * q + 3]};
+            if (act >= 0 && q == (act >> 4)) {
+                const uint32_t m = 0xffu << ((act & 3) * 8);
+                const int k = (act >> 2) & 3;
+                const bool alive_now = (cur[act >> 5] >> (act & 31)) & 1u;     // cur holds the toggled plane
+                s[k] = (s[k] & ~m) | ((masked && !alive_now) ? 0u : (spawn4 & m));
+            }
+            const uint32_t m = mix[q];
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t sv = (m >> (8 * k)) & 0xfu, bn = (m >> (8 * k + 4)) & 0xfu;
+                s[k] = stable_update4_rule(rule, s[k], table[sv][0], table[bn][0], spawn4, max4, min4, empty4);
+                for (int b = 0; b < 4; ++b) acc += (int8_t)(s[k] >> (8 * b));
+                sp[4 * q + k] = s[k];
+            }
+        }
+        if (reward_out) reward_out[e] = acc;
+        if (alive_out) alive_out[e] = pop;
+    }
+    return err;
+}
+
 }  // extern "C"
