@@ -20,8 +20,9 @@ Deliberate deviations (all documented in DESIGN.md section 2):
   * shallow views are pinned host mirrors kept up to date by every state-changing call
     (reads see live state, aliasing `state is n_state` holds, CGL/main.py:60,70); writes INTO a
     shallow view do not reach the device -- use toggle_state / update_state / load;
-  * a single-index toggle_state is applied lazily: it is fused into the next step() launch, or applied
-    by the next other call into the env; a shallow view shows it from that call on;
+  * a single-index toggle_state is applied lazily: it is passed BY VALUE to the next step() launch (one kernel
+    does toggle + generation + stability + reward and stores the observation straight into the pinned mirror,
+    cgl_sim_step), or applied by the next other call into the env; a shallow view shows it from that call on;
   * plain step() calls are deferred while no shallow view is live and executed together (one on-chip
     launch for the whole run of steps) when the state is next observed or changed -- same results, and
     the reference's `for _ in range(iters): env.step()` loop costs one launch.
@@ -169,14 +170,37 @@ class sim:
         self._m_stable = self._m_stable_t.numpy()
         self._world_fresh = self._stable_fresh = False
         self._world_live = self._stable_live = False       # a shallow view has been handed out
-        # one pinned word each for the fused step: the kernel reads the pending action from and writes
-        # the reward to device-mapped host memory -- a step is ONE launch without staging copies
-        self._m_action_t = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self._m_reward_t = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self._m_action, self._m_reward = self._m_action_t.numpy(), self._m_reward_t.numpy()
+        # result block of the one-launch step (cgl_sim_step): the kernel writes reward, live count and then the
+        # step's sequence number into this pinned, host-mapped memory; the host polls the sequence word
+        self._res_t = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._res = self._res_t.numpy()
+        self._seq = 0
+        self._pending_seq = None                            # sequence number of a step whose results are in flight
         self._pending = None                                # scalar toggle deferred into the next step()
         self._lazy_steps = 0                                # plain steps not yet executed (see step())
-        self._reward_valid = False                          # _m_reward holds reward() of the current state
+        self._reward_valid = False                          # _res[0] holds reward() of the current state
+        self._alive_valid = False                           # _res[1] holds alive() of the current state
+        self._fast = self.side <= int(self._b._lib.cgl_sim_step_max_side())
+        self._fast_args = {}
+
+    def _invalidate(self):
+        """The state changed by something other than a step: cached reward / live count are stale."""
+        self._reward_valid = self._alive_valid = False
+
+    def _wait(self):
+        """Block until the last one-launch step has delivered observation mirror, reward and live count: poll the
+        sequence word the kernel writes last (no stream synchronisation, no copy)."""
+        seq = self._pending_seq
+        if seq is None:
+            return
+        res, spins = self._res, 0
+        while res[2] != seq:
+            spins += 1
+            if spins > 200000:                              # ~50 ms: something is wrong, let CUDA report it
+                self._torch.cuda.current_stream(self._dev).synchronize()
+                if res[2] != seq:
+                    raise RuntimeError("CGL.sim: the step kernel finished without delivering its results")
+        self._pending_seq = None
 
     def _flush(self):
         """Bring the device state up to date with everything the caller has asked for so far: run the plain
@@ -185,8 +209,9 @@ class sim:
         self._run_lazy()
         if self._pending is not None:
             a, self._pending = self._pending, None
+            self._wait()
             self._b.toggle(self._torch.tensor([[a]], dtype=self._torch.int32, device=self._dev))
-            self._reward_valid = False
+            self._invalidate()
             self._changed()
 
     def _run_lazy(self):
@@ -194,10 +219,11 @@ class sim:
         if n == 1:
             self._step_now()
         elif n > 1:                 # the whole run of plain steps is ONE launch with the env resident on chip
+            self._wait()
             with self._torch.cuda.device(self._dev):
                 _, rew, _ = self._b.run(n)
-                self._m_reward_t.copy_(rew, non_blocking=True)
-            self._reward_valid = True
+                self._res_t[0:1].copy_(rew)                 # blocking copy: the run is long, the sync is not
+            self._reward_valid, self._alive_valid = True, False
             self._changed()
 
     def _changed(self, world=True, stable=True):
@@ -219,8 +245,11 @@ class sim:
 
     def _sync_stable(self):
         if not self._stable_fresh:
+            self._wait()
             self._m_stable_t.copy_(self._b.stable.view(-1))
             self._stable_fresh = True
+        else:
+            self._wait()                                    # the mirror is being written by the step in flight
         return self._m_stable
 
     # reference attribute names (read access): live host views of the device state
@@ -262,27 +291,62 @@ class sim:
         self.count += 1
         if self._pending is None and not (self._world_live or self._stable_live) and self._can_defer:
             self._lazy_steps += 1
-            self._reward_valid = False
+            self._invalidate()
             self._world_fresh = self._stable_fresh = False
             return
         self._run_lazy()
         self._step_now()
 
     def _step_now(self):
-        # toggle (if one is pending) + generation + stability + reward in one launch; the action word is
-        # read from, and the reward written to, pinned host memory
-        actions_ptr = 0
+        """toggle (if one is pending) + generation + stability + reward + live count in ONE launch
+        (cgl_sim_step): the action travels by value, the new observation is stored by the kernel into the pinned
+        mirror as well, and reward / live count / sequence number into the pinned result block."""
+        a = self.size                                       # "do nothing"
         if self._pending is not None:
-            self._m_action[0] = self._pending
-            self._pending = None
-            actions_ptr = self._m_action_t.data_ptr()
-        with self._torch.cuda.device(self._dev):
-            if self._b.fused:       # one thread per env writes the reward: straight into the pinned word
-                self._b.step_ptrs(actions_ptr, self._m_reward_t.data_ptr())
-            else:                   # generic kernels accumulate it with atomics: keep those on the device
-                self._b.step_ptrs(actions_ptr, self._b._reward.data_ptr())
-                self._m_reward_t.copy_(self._b._reward, non_blocking=True)
-        self._reward_valid = True
+            a, self._pending = self._pending, None
+        b = self._b
+        if not self._fast:
+            return self._step_now_batched(a)
+        key = b._wa.data_ptr()
+        args = self._fast_args.get(key)
+        if args is None:
+            import ctypes
+            from cgl_b200.batched import DEAD_RULES
+            V = ctypes.c_void_p
+            args = (V(b._wa.data_ptr()), V(b._wb.data_ptr()), V(b.stable.data_ptr()), self.side,
+                    b.spawn, b.stable_max, DEAD_RULES[b.dead_rule], b.empty, b.empty_min, int(b.masked_toggle),
+                    V(self._m_stable_t.data_ptr()), V(self._res_t.data_ptr()), b._lib.cgl_sim_step)
+            self._fast_args[key] = args
+        self._wait()                                        # one step in flight at a time (the result block is shared)
+        self._seq = seq = (self._seq + 1) & 0x3fffffff
+        torch = self._torch
+        if torch.cuda.current_device() != self._dev.index:
+            torch.cuda.set_device(self._dev)
+        rc = args[12](args[0], args[1], args[2], args[3], a, args[4], args[5], args[6], args[7], args[8], args[9],
+                      args[10], args[11], seq, b._stream())
+        if rc:
+            from cgl_b200 import native
+            native.check(rc, "cgl_sim_step")
+        b._wa, b._wb = b._wb, b._wa
+        b.count += 1
+        b.launches += 1
+        self._pending_seq = seq
+        self._reward_valid = self._alive_valid = True
+        self._stable_fresh = True                           # valid once _wait() has seen the sequence number
+        self._world_fresh = False
+        if self._stable_live:
+            self._wait()                                    # a live view must show the new state when step() returns
+        if self._world_live:
+            self._sync_world()
+
+    def _step_now_batched(self, a):
+        """Sides above cgl_sim_step's limit: the batched kernels (toggle, generation, stability), then copies."""
+        torch, b = self._torch, self._b
+        with torch.cuda.device(self._dev):
+            act = None if a == self.size else torch.tensor([a], dtype=torch.int32, device=self._dev)
+            _, rew, _ = b.step(act)
+            self._res_t[0:1].copy_(rew)
+        self._reward_valid, self._alive_valid = True, False
         self._changed()
 
     @property
@@ -295,12 +359,13 @@ class sim:
         the first step that leaves the world unchanged (CGL_action+/validate.py:133-139).  Returns the
         number of steps executed; `count` advances by it."""
         self._flush()
+        self._wait()
         with self._torch.cuda.device(self._dev):
             _, rew, steps = self._b.run(int(iters), until_fixed=until_fixed)
             n = int(steps.item())
-            self._m_reward[0] = int(rew.item())
+            self._res[0] = int(rew.item())
         self.count += n
-        self._reward_valid = True
+        self._reward_valid, self._alive_valid = True, False
         self._changed()
         return n
 
@@ -322,20 +387,24 @@ class sim:
         """np.int32 sum of the stability vector (CGL/CGL.py:255-256)."""
         self._flush()
         if self._reward_valid:                              # written by the last step's kernel
-            self._torch.cuda.current_stream(self._dev).synchronize()
-            return np.int32(self._m_reward[0])
+            self._wait()
+            return np.int32(self._res[0])
         return np.int32(self._b.reward().item())
 
     def alive(self):
         """np.uint32 number of live cells (CGL/CGL.py:259-260)."""
         self._flush()
+        if self._alive_valid:                               # written by the last step's kernel
+            self._wait()
+            return np.uint32(self._res[1])
         return np.uint32(self._b.alive().item())
 
     def reset(self):
         """Back to the initial state; `count` is not reset (CGL/CGL.py:264-266)."""
         self._pending = None
         self._lazy_steps = 0                                # whatever was still owed is overwritten by the reset
-        self._reward_valid = False
+        self._wait()
+        self._invalidate()
         self._b.reset()
         self._changed()
 
@@ -394,6 +463,8 @@ class sim:
                              f"Was given size={temp.size} and side={side} but was expecting size={self.size} and side={self.side}.")
         cells = self._validated_cells(temp)
         self._flush()
+        self._wait()
+        self._alive_valid = False
         self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
         self._changed(world=True, stable=False)
 
@@ -401,6 +472,19 @@ class sim:
         """Toggle the listed cells and set their stability to spawn (CGL/CGL.py:322-328).
         Duplicates toggle once; the scalar `size` is the silent "do nothing"; anything else out of
         range raises ValueError."""
+        if isinstance(indx, (int, np.integer)) and not isinstance(indx, bool):
+            # the DQN loop's case (CGL/main.py:66-67): one index, then step().  The toggle is deferred and
+            # travels by value into that launch.  Every other call into the env applies it first (_flush), so
+            # the only place it is not yet visible is a shallow numpy view read before the next call.
+            a = int(indx)
+            if 0 <= a < self.size:
+                self._flush()                               # an earlier deferred toggle goes first
+                self._pending = a
+                self._invalidate()
+            elif a != self.size:
+                raise ValueError("Not all indexes are valid!\nIndexes must be positive and less than the size of the "
+                                 f"state {self.size}.")
+            return
         indx = np.array(indx)
         if np.all(indx < self.size) and np.all(indx >= 0):
             if indx.dtype.kind not in "iu":
@@ -408,14 +492,12 @@ class sim:
             flat = np.ascontiguousarray(indx.reshape(-1), dtype=np.int32)
             self._flush()                                   # an earlier deferred toggle goes first
             if flat.size == 1:
-                # the DQN loop's case (CGL/main.py:66-67): one index, then step() -- deferred and fused
-                # into that launch.  Every other call into the env applies it first (_flush), so the
-                # only place it is not yet visible is a shallow numpy view read before the next call.
                 self._pending = int(flat[0])
-                self._reward_valid = False
+                self._invalidate()
             elif flat.size:
+                self._wait()
                 self._b.toggle(self._torch.from_numpy(flat).to(self._dev)[None, :])
-                self._reward_valid = False
+                self._invalidate()
                 self._changed()
         elif indx != self.size:     # an array with >1 element raises ValueError here, like the reference
             raise ValueError("Not all indexes are valid!\nIndexes must be positive and less than the size of the "
@@ -448,7 +530,9 @@ class sim:
         from cgl_b200.batched import BatchedSim
         self._pending = None
         self._lazy_steps = 0
-        self._reward_valid = False
+        self._wait()
+        self._invalidate()
+        self._fast_args.clear()                             # the launch arguments cache the constants
         self.stableStabilityFactor = stableStabilityFactor
         self.spawnStabilityFactor = spawnStabilityFactor
         resized = side != self.side

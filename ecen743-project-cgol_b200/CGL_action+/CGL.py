@@ -81,7 +81,8 @@ class sim(_base.sim):
         initState and initStable are left alone like in the fork."""
         self._pending = None
         self._lazy_steps = 0
-        self._reward_valid = False
+        self._wait()
+        self._invalidate()
         np.random.seed(seed)
         cells = np.random.randint(2, size=self.size, dtype=np.uint8)
         self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
@@ -108,6 +109,8 @@ class sim(_base.sim):
                              f"Was given size={temp.size} but was expecting size={self.size} and side={self.side}.")
         cells = self._validated_cells(temp)
         self._flush()
+        self._wait()
+        self._alive_valid = False
         self._b.set_state(self._torch.from_numpy(cells)[None, :].to(self._dev))
         if newStability is not None:
             stab = np.ascontiguousarray(newStability.flatten().astype(np.int8))
@@ -129,6 +132,7 @@ class sim(_base.sim):
         self.empty = empty
         super().load(newState, newstable, side, count, spawnStabilityFactor, stableStabilityFactor)
         self._b.set_factors(spawnStabilityFactor, stableStabilityFactor, empty)
+        self._fast_args.clear()
 
 
 # Maximum-density still-life optima for n x n boards, n = 0..60 (Chu & Stuckey 2012, table 7).

@@ -82,6 +82,7 @@ class BatchedSim:
 
         with torch.cuda.device(self.device):
             B, size, W = n_envs, self.size, self.W
+            self._alarm = native.alarm()                    # host-mapped alarm words, installed on this device
             self._wa = torch.zeros((B, side, W), dtype=torch.int32, device=self.device)
             self._wb = torch.zeros_like(self._wa)
             self.stable = torch.zeros((B, size), dtype=torch.int8, device=self.device)
@@ -200,6 +201,8 @@ class BatchedSim:
             if (reward_out.dtype != torch.int32 or reward_out.device != self.device
                     or not reward_out.is_contiguous() or reward_out.numel() != self.n_envs):
                 raise TypeError("reward_out must be a contiguous int32 tensor [n_envs] on the env's device")
+        if self._alarm[1]:                                  # a chained step gave up on its token (no sync needed to see it)
+            native.check_alarm()
         src = self._wa.data_ptr()
         a_ptr = 0 if actions is None else actions.data_ptr()
         s_in = self.stable.data_ptr()
@@ -286,28 +289,6 @@ class BatchedSim:
         alive = self.alive()
         return torch.stack([self.size - alive, alive], dim=1)
 
-    def step_ptrs(self, actions_ptr: int, reward_ptr: int) -> None:
-        """step() with raw pointers: `actions_ptr` (0 = no actions) and `reward_ptr` may be device memory
-        or device-mapped pinned host memory -- the single-env facade passes pinned words so that a step is
-        one launch with no staging copies."""
-        if self._ext:
-            rc = self._lib.cgl_env_step_rule(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                             native.dptr(self.stable), self.n_envs, self.side,
-                                             ctypes.c_void_p(actions_ptr), self.spawn, self.stable_max,
-                                             DEAD_RULES[self.dead_rule], self.empty, self.empty_min,
-                                             int(self.masked_toggle), ctypes.c_void_p(reward_ptr), None,
-                                             native.dptr(self._err), None, 0, 0, self._stream())
-        else:
-            rc = self._lib.cgl_env_step(native.dptr(self._wa), native.dptr(self._wb), native.dptr(self.stable),
-                                        self.n_envs, self.side, ctypes.c_void_p(actions_ptr), self.spawn,
-                                        self.stable_max, ctypes.c_void_p(reward_ptr), None, native.dptr(self._err),
-                                        self._stream())
-        if rc:
-            native.check(rc, "cgl_env_step")
-        self._wa, self._wb = self._wb, self._wa
-        self.count += 1
-        self.launches += self._lib.cgl_env_step_launches(self.side, int(actions_ptr != 0))
-
     def set_factors(self, spawnStabilityFactor: int, stableStabilityFactor: int, empty: int | None = None) -> None:
         """Change the stability constants (sim.load, CGL/CGL.py:348-349); cached launch arguments are dropped."""
         self.spawn, self.stable_max = spawnStabilityFactor, stableStabilityFactor
@@ -323,9 +304,11 @@ class BatchedSim:
         err = int(self._err.item())
         if err & 2:
             self._err.zero_()
+            self._alarm[1] = 0
             raise native.CglNativeError("chained env step: a plane token never arrived (state planes out of sync)")
         if err != 0:
             self._err.zero_()
+            self._alarm[0] = 0
             raise ValueError(f"Not all indexes are valid!\nIndexes must be positive and less than the size of the state {self.size}.")
 
     def toggle(self, idx: torch.Tensor) -> None:

@@ -27,6 +27,9 @@ _vp, _u64, _u32, _i = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.
 SIGNATURES = {
     "cgl_abi_version": (_i, []),
     "cgl_last_error": (ctypes.c_char_p, []),
+    "cgl_alarm_words": (_i, [ctypes.POINTER(ctypes.POINTER(ctypes.c_int))]),
+    "cgl_set_wait_timeout_ms": (_i, [_u32]),
+    "cgl_test_fault": (_i, [_i]),
     "cgl_device_count": (_i, [ctypes.POINTER(_i)]),
     "cgl_device_info": (_i, [_i, ctypes.c_char_p, _i, ctypes.POINTER(_i), ctypes.POINTER(_i),
                              ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
@@ -44,6 +47,8 @@ SIGNATURES = {
     "cgl_toggle_rule": (_i, [_vp, _vp, _u64, _u32, _vp, _u32, _i, _i, _vp, _vp]),
     "cgl_init_stable_rule": (_i, [_vp, _vp, _u64, _u32, _i, _i, _vp]),
     "cgl_env_step_io": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "cgl_sim_step": (_i, [_vp, _vp, _vp, _u32, ctypes.c_int32, _i, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp]),
+    "cgl_sim_step_max_side": (_u32, []),
     "cgl_env_step_is_fused": (_i, [_u32]),
     "cgl_env_step_launches": (_i, [_u32, _i]),
     "cgl_life_step": (_i, [_vp, _vp, _u64, _u32, _u32, _i, _vp, _vp]),
@@ -106,6 +111,36 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().cgl_last_error().decode("utf-8", "replace")
         raise CglNativeError(f"{what or 'libcgl_b200'} failed (rc={rc}): {msg}")
+
+
+ALARM_NAMES = ("an action / toggle index outside [0, size] was ignored",
+               "chained env step: a plane token never arrived (state planes out of sync)",
+               "life mode: a strip token of the previous launch never arrived",
+               "halo exchange: a ring neighbour never delivered its rows")
+_alarm = None
+
+
+def alarm():
+    """The library's alarm words as a live numpy view (int32[4], host-mapped pinned memory; see cgl_alarm_words in
+    include/cgl_b200.h).  Also installs them on the current CUDA device.  Reading costs no synchronisation."""
+    global _alarm
+    import numpy as np
+    p = ctypes.POINTER(ctypes.c_int)()
+    check(load().cgl_alarm_words(ctypes.byref(p)), "cgl_alarm_words")
+    if _alarm is None:
+        _alarm = np.ctypeslib.as_array(p, shape=(4,))
+    return _alarm
+
+
+def check_alarm(clear: bool = True) -> None:
+    """Raise if a kernel gave up on a device-side wait (words 1..3).  Word 0 (invalid action) is left to
+    BatchedSim.check_actions, which turns it into the reference's ValueError."""
+    a = _alarm if _alarm is not None else alarm()
+    if a[1] or a[2] or a[3]:
+        msgs = [ALARM_NAMES[i] for i in (1, 2, 3) if a[i]]
+        if clear:
+            a[1:] = 0
+        raise CglNativeError("; ".join(msgs))
 
 
 def dptr(t) -> ctypes.c_void_p:

@@ -42,14 +42,20 @@ __global__ void halo_push_kernel(const uint4 *__restrict__ src, uint4 *__restric
     }
 }
 
-__device__ __forceinline__ void spin_until(const uint32_t *flag, uint32_t seq)
+// Wait until *flag - seq >= 0 (acquire, system scope).  Bounded: a peer that died or never launched its side of
+// the exchange raises the halo alarm word after g_wait_ns instead of hanging this GPU until a device reset.
+__device__ __forceinline__ bool spin_until(const uint32_t *flag, uint32_t seq)
 {
-    uint32_t v;
+    uint32_t v, spins = 0;
+    unsigned long long t0 = 0;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - seq) >= 0) break;
+        if ((int32_t)(v - seq) >= 0) return true;
         __nanosleep(64);
-    } while (true);
+        if (spins == 0) t0 = globaltimer_ns();
+    } while ((++spins & 127u) != 0 || !wait_expired(t0, ALARM_HALO));
+    raise_alarm(ALARM_HALO);
+    return false;
 }
 
 __global__ void halo_wait_kernel(const uint32_t *flag, uint32_t seq) { spin_until(flag, seq); }
@@ -58,8 +64,10 @@ __global__ void halo_wait_kernel(const uint32_t *flag, uint32_t seq) { spin_unti
 __global__ void halo_wait_copy_kernel(const uint32_t *flag, uint32_t seq, const uint4 *__restrict__ src,
                                       uint4 *__restrict__ dst, uint64_t n_vec)
 {
-    if (threadIdx.x == 0) spin_until(flag, seq);
+    __shared__ int arrived;
+    if (threadIdx.x == 0) arrived = spin_until(flag, seq);
     __syncthreads();
+    if (!arrived) return;                       // timed out: the ghost rows keep their old contents, alarm raised
     for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -82,18 +90,68 @@ __global__ void __launch_bounds__(1024) halo_exchange_kernel(HaloSide up, HaloSi
     for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) s.peer_landing[i] = s.src[i];
     __threadfence_system();
     __syncthreads();
+    __shared__ int arrived;
     if (threadIdx.x == 0) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.peer_flag), "r"(seq) : "memory");
-        spin_until(s.my_flag, seq);
+        arrived = spin_until(s.my_flag, seq);
     }
     __syncthreads();
+    if (!arrived) return;                       // timed out: alarm raised, nothing copied from the landing zone
     for (uint64_t i = threadIdx.x; i < n_vec; i += blockDim.x) s.ghost[i] = __ldcg(s.my_landing + i);
+}
+
+CGL_DEFINE_TU_HOOKS(api)
+
+// ---- alarm words + wait bound (see cgl_internal.cuh) ------------------------------------------------------
+static int *g_alarm_host = nullptr, *g_alarm_dev = nullptr;
+static unsigned long long g_wait_ns_host = 2000000000ull;
+static bool g_hooks_set[64] = {};
+
+static int apply_hooks()
+{
+    int rc;
+    if ((rc = set_hooks_env(g_alarm_dev, g_wait_ns_host))) return rc;
+    if ((rc = set_hooks_life_tb(g_alarm_dev, g_wait_ns_host))) return rc;
+    return set_hooks_api(g_alarm_dev, g_wait_ns_host);
 }
 
 }  // namespace cgl
 
 using namespace cgl;
+
+extern "C" int cgl_alarm_words(int **host_words_out)
+{
+    CGL_REQUIRE(host_words_out, CGL_E_BADARG, "cgl_alarm_words: null");
+    if (g_alarm_host == nullptr) {
+        void *h = nullptr, *d = nullptr;
+        CGL_CUDA(cudaHostAlloc(&h, CGL_ALARM_WORDS * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h, 0, CGL_ALARM_WORDS * sizeof(int));
+        CGL_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+        g_alarm_host = static_cast<int *>(h);
+        g_alarm_dev = static_cast<int *>(d);
+    }
+    int dev = 0;
+    CGL_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !g_hooks_set[dev]) {
+        int rc = apply_hooks();
+        if (rc) return rc;
+        g_hooks_set[dev] = true;
+    }
+    *host_words_out = g_alarm_host;
+    return 0;
+}
+
+extern "C" int cgl_set_wait_timeout_ms(uint32_t ms)
+{
+    g_wait_ns_host = (unsigned long long)ms * 1000000ull;
+    int dev = 0;
+    CGL_CUDA(cudaGetDevice(&dev));
+    int rc = apply_hooks();                         // current device now; other devices at their next cgl_alarm_words
+    for (int i = 0; i < 64; ++i) g_hooks_set[i] = false;
+    if (rc == 0 && dev >= 0 && dev < 64) g_hooks_set[dev] = true;
+    return rc;
+}
 
 extern "C" int cgl_halo_exchange(const uint32_t *top_src, const uint32_t *bot_src, uint32_t *peer_up_landing,
                                  uint32_t *peer_dn_landing, uint32_t *peer_up_flag, uint32_t *peer_dn_flag,

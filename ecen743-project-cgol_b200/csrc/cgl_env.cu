@@ -35,8 +35,8 @@ struct EnvCfg {
     static constexpr int THREADS = TPE * EPC;
     static constexpr int CPT = NCHUNK / TPE;      // chunks per thread
     static constexpr int UNR = CPT < 8 ? CPT : 8; // chunks in flight per thread
-    // [<= 4 KB align slack][mask tables 4 KB][per env: cur WPE*4 | mix WPE*8][per env: 2 ints]
-    static constexpr int SMEM = 4096 + 4096 + EPC * (WPE * 4 + WPE * 8) + EPC * 8;
+    // [<= 4 KB align slack][mask tables 4 KB][per env: cur WPE*4 | mix WPE*8][per env: 4 ints]
+    static constexpr int SMEM = 4096 + 4096 + EPC * (WPE * 4 + WPE * 8) + EPC * 16;
     static_assert(S % 32 == 0 && NCHUNK % TPE == 0 && WPE % 4 == 0, "unsupported side");
 };
 
@@ -119,39 +119,60 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     const int t = threadIdx.x % C::TPE;
     uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw + 4096) + g * (C::WPE * 3);
     uint32_t *mix = cur + C::WPE;                 // 2 words per world word
-    int *red = reinterpret_cast<int *>(smem_raw + 4096 + C::EPC * C::WPE * 12) + g * 2;
+    int *red = reinterpret_cast<int *>(smem_raw + 4096 + C::EPC * C::WPE * 12) + g * 4;   // reward, alive, token ok
 
     const uint32_t e = blockIdx.x * C::EPC + g;
-    const bool active = e < n_envs;
+    bool active = e < n_envs;
 
     // Programmatic dependent launch: the NEXT launch's CTAs may take the SM slots this grid frees in
-    // its tail (hides the launch latency between back-to-back steps); they wait here until this grid
-    // has completed.  The stability loads stay the first thing a CTA does after that -- a CTA's
-    // life is latency-bound, and the mask-table fill below overlaps with those loads.
-    cudaTriggerProgrammaticLaunchCompletion();
+    // its tail (hides the launch latency between back-to-back steps).  The stability loads stay the first
+    // thing a CTA does after its wait -- a CTA's life is latency-bound, and the mask-table fill overlaps
+    // with them.
     if (epoch == nullptr) {
-        cudaGridDependencySynchronize();
+        cudaTriggerProgrammaticLaunchCompletion();
+        cudaGridDependencySynchronize();            // plain form: wait for the whole previous grid
     } else {
         // Chained steps: env e of this launch depends only on env e of the previous launch, which
         // published epoch[e] = want (the id of the plane this launch reads) when it was done.  The
         // next launch's first CTAs therefore start while the previous launch's last CTAs are still
         // running (ramp-up overlaps the tail); the spin almost never iterates because CTAs are
         // dispatched in env order.  The token load is issued first and the mask tables are filled in
-        // its shadow.  The spin is bounded: a token that never arrives (caller bug) raises bit 1 of
-        // the error flag instead of hanging the GPU.
+        // its shadow.
+        //
+        // Two plane ids are enough BECAUSE this CTA allows its dependents to launch only after its own wait
+        // has succeeded: launch n+2 can start only when every CTA of launch n+1 has triggered, i.e. has seen
+        // the token of launch n for its env, i.e. when launch n has completely finished.  So at most two
+        // consecutive chained launches are ever in flight and a token value cannot be mistaken for the one
+        // two launches back (which it could if the trigger came first -- with small batches three grids fit
+        // on the GPU at once).
+        //
+        // The wait is bounded (g_wait_ns, cgl_set_wait_timeout_ms).  A token that never arrives (caller bug,
+        // a predecessor that was never launched) sets bit 1 of the error flag, raises the alarm word and
+        // SKIPS the env: no plane is written and no token published, so nothing is computed from stale
+        // planes and every later chained step of that env fails the same way (fast: see wait_expired).
         uint32_t v = want;
         if (t == 0 && active) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
         for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
             const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
             tables[i] = (i & 32) ? (m & spawn4) : m;
         }
-        if (t == 0 && active) {
-            uint32_t spins = 0;
-            while (v != want && ++spins < (1u << 17))
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
-            if (v != want && err_flag != nullptr) atomicOr(err_flag, 2);
+        if (t == 0) {
+            if (active && v != want) {
+                const unsigned long long t0 = globaltimer_ns();
+                uint32_t spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
+                } while (v != want && ((++spins & 255u) != 0 || !wait_expired(t0, ALARM_ENV_TOKEN)));
+                if (v != want) {
+                    if (err_flag != nullptr) atomicOr(err_flag, 2);
+                    raise_alarm(ALARM_ENV_TOKEN);
+                }
+            }
+            red[2] = (v == want);
         }
         __syncthreads();
+        cudaTriggerProgrammaticLaunchCompletion();
+        active = active && red[2] != 0;
     }
 
     // ---- phase 0: stability loads in flight before anything else --------------------------
@@ -175,7 +196,10 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     if (active && actions != nullptr) {
         int a = actions[e];
         if (a >= 0 && a < C::SIZE) act = a;
-        else if (a != C::SIZE && t == 0 && err_flag != nullptr) atomicOr(err_flag, 1);
+        else if (a != C::SIZE && t == 0) {
+            if (err_flag != nullptr) atomicOr(err_flag, 1);
+            raise_alarm(ALARM_BAD_ACTION);
+        }
     }
     // cell index == bit index because a row is exactly W full words
     const int act_word = act >> 5;
@@ -300,26 +324,28 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             }
         }
     }
-    if (epoch != nullptr) {
-        // publish: barrier (all stores of this env issued), then ONE release store -- release is
-        // cumulative over what the barrier ordered before it (the grid-sync idiom)
-        __syncthreads();
-        if (t == 0 && active) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(epoch + e), "r"(publish) : "memory");
-    }
-    if (reward_out != nullptr || alive_out != nullptr) {
+    // ---- reward / alive, then the token --------------------------------------------------------
+    // Order matters: the env's thread 0 stores reward and alive BEFORE it publishes the token, so the next
+    // launch's CTA of this env (which may already be spinning on it) can never be overtaken by these stores.
+    const bool want_red = reward_out != nullptr || alive_out != nullptr;
+    if (want_red) {
         acc = __reduce_add_sync(0xffffffffu, acc);
         pop = __reduce_add_sync(0xffffffffu, pop);
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&red[0], acc);
             atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
         }
-        __syncthreads();
-        if (active && t == 0) {
-            if (reward_out != nullptr) reward_out[e] = red[0];
-            if (alive_out != nullptr) alive_out[e] = (uint32_t)red[1];
-        }
+    }
+    if (want_red || epoch != nullptr) __syncthreads();      // all stores of this env issued, sums complete
+    if (active && t == 0) {
+        if (reward_out != nullptr) reward_out[e] = red[0];
+        if (alive_out != nullptr) alive_out[e] = (uint32_t)red[1];
+        // ONE release store: release is cumulative over what the barrier ordered before it (the grid-sync idiom)
+        if (epoch != nullptr) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(epoch + e), "r"(publish) : "memory");
     }
 }
+
+CGL_DEFINE_TU_HOOKS(env)
 
 // CGL_ENV_PDL=0 turns programmatic dependent launch off (tuning / debugging).
 static bool pdl_enabled()
@@ -410,6 +436,7 @@ __global__ void toggle_kernel(uint32_t *__restrict__ world, int8_t *__restrict__
             const int64_t a = my[j];
             if (a < 0 || (uint64_t)a > size) {
                 if (err_flag != nullptr) atomicOr(err_flag, 1);
+                raise_alarm(ALARM_BAD_ACTION);
                 continue;
             }
             if ((uint64_t)a == size) continue;               // "do nothing" action

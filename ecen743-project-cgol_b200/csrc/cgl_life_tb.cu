@@ -53,13 +53,18 @@ struct HaloCtx {
 // last strips of launch j finish, which removes the cost of a partly filled last wave.
 struct ChainCtx { uint32_t *tokens; uint32_t want; uint32_t cap; };
 
-// Spin until *ctr - target >= 0 (acquire, system scope); lane 0 polls, the warp follows.
-__device__ __forceinline__ void wait_counter(const uint32_t *ctr, uint32_t target)
+// Spin until *ctr - target >= 0 (acquire, system scope); every exit is a warp vote, so the warp stays
+// convergent.  Bounded by g_wait_ns: false = the neighbour never arrived (alarm raised by the caller).
+__device__ __forceinline__ bool wait_counter(const uint32_t *ctr, uint32_t target)
 {
-    uint32_t v;
-    do {
+    uint32_t v, spins = 0;
+    unsigned long long t0 = 0;
+    while (true) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (__any_sync(0xffffffffu, (int32_t)(v - target) < 0));      // warp-uniform exit
+        if (!__any_sync(0xffffffffu, (int32_t)(v - target) < 0)) return true;      // warp-uniform exit
+        if (spins == 0) t0 = globaltimer_ns();
+        if ((++spins & 255u) == 0 && __any_sync(0xffffffffu, wait_expired(t0, ALARM_HALO))) return false;
+    }
 }
 
 // Predicated store: `if (ok && a < b) *p = v` as ONE predicated STG.  Written in PTX on purpose: the
@@ -99,6 +104,7 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
     uint32_t rb = warp / n_cgroups;
     const bool warp_ok = rb < n_rblocks;
     rb = warp_ok ? rb : n_rblocks - 1;
+    bool wait_ok = true;                                       // warp-uniform: false once a bounded wait expired
 
     if (!HALO && chain.tokens != nullptr) {                    // kernel-uniform branch
         cudaTriggerProgrammaticLaunchCompletion();
@@ -113,16 +119,24 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
         }
         const uint32_t *tp = chain.tokens + (need ? (uint32_t)nrb * n_cgroups + ncg : 0u);
         uint32_t v, spins = 0;
-        bool ok;
-        do {
+        unsigned long long t0 = 0;
+        while (true) {                                         // every exit is a warp vote (see above)
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tp) : "memory");
-            ok = !need || (int32_t)(v - chain.want) >= 0;
-        } while (!__all_sync(0xffffffffu, ok) && ++spins < (1u << 17));      // warp-uniform exit, bounded
+            if (__all_sync(0xffffffffu, !need || (int32_t)(v - chain.want) >= 0)) break;
+            if (spins == 0) t0 = globaltimer_ns();
+            if ((++spins & 255u) == 0 && __any_sync(0xffffffffu, wait_expired(t0, ALARM_LIFE_TOKEN))) {
+                // a neighbour strip of the previous launch never finished: store nothing, publish nothing
+                // (later launches of the chain then fail the same way) and tell the host
+                wait_ok = false;
+                if (lane == 0) raise_alarm(ALARM_LIFE_TOKEN);
+                break;
+            }
+        }
     }
 
     const int wi = (int)(cg * TB_COLS + lane) - 1;             // word column of this lane (may be -1 or >= W)
     const uint32_t wcol = wi < 0 ? (uint32_t)(wi + (int)W) : ((uint32_t)wi >= W ? (uint32_t)wi - W : (uint32_t)wi);
-    const bool store_ok = warp_ok && lane >= 1 && lane <= TB_COLS && (uint32_t)wi < W;
+    bool store_ok = warp_ok && wait_ok && lane >= 1 && lane <= TB_COLS && (uint32_t)wi < W;
 
     const int r0 = (int)(rb * rpt);
     const int r1 = (r0 + (int)rpt < (int)rows) ? r0 + (int)rpt : (int)rows;
@@ -146,8 +160,14 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
         push_dn = warp_ok && (uint32_t)r0 < hc.store_hi && (uint32_t)r1 + hc.depth > hc.store_hi;
         const bool reads_up = r0 - K < (int)hc.store_lo, reads_dn = (uint32_t)(r1 + K) > hc.store_hi;
         // unconditional (branch-free): strips that need nothing wait for target 0, i.e. not at all
-        wait_counter(hc.wait_up, (reads_up || push_up) ? hc.wait_up_target : 0u);
-        wait_counter(hc.wait_dn, (reads_dn || push_dn) ? hc.wait_dn_target : 0u);
+        const bool up_ok = wait_counter(hc.wait_up, (reads_up || push_up) ? hc.wait_up_target : 0u);
+        const bool dn_ok = wait_counter(hc.wait_dn, (reads_dn || push_dn) ? hc.wait_dn_target : 0u);
+        if (!(up_ok && dn_ok)) {                               // a ring neighbour never arrived: see above
+            wait_ok = false;
+            store_ok = false;
+            push_up = push_dn = false;
+            if (lane == 0) raise_alarm(ALARM_HALO);
+        }
     }
 
     const uint32_t owned_rows = HALO ? hc.store_hi - hc.store_lo : 0u;
@@ -203,7 +223,7 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
     if (!HALO && chain.tokens != nullptr) {
         __threadfence();                             // this strip's rows are visible device-wide ...
         __syncwarp();
-        if (lane == 0 && warp_ok)                    // ... before its token is published
+        if (lane == 0 && warp_ok && wait_ok)         // ... before its token is published
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain.tokens + rb * n_cgroups + cg),
                          "r"(chain.want + 1) : "memory");
     }
@@ -358,12 +378,24 @@ static uint32_t *chain_tokens(cudaStream_t st, uint32_t rows, uint32_t cols, uin
     return tb->p;
 }
 
+CGL_DEFINE_TU_HOOKS(life_tb)
+
 }  // namespace cgl
 
 using namespace cgl;
 
 extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,
                              uint32_t cols, int wrap_rows, uint32_t *alive_out, cgl_stream_t stream);
+
+// Test hook (tests/test_gpu_waits.py): which = 1 makes the next chained cgl_life_run wait for strip tokens that
+// are never published, so that the bounded wait, the alarm word and the "store nothing" path can be exercised.
+static int g_fault_next_chain = 0;
+extern "C" int cgl_test_fault(int which)
+{
+    CGL_REQUIRE(which == 1, CGL_E_BADARG, "cgl_test_fault: unknown fault %d", which);
+    g_fault_next_chain = 1;
+    return 0;
+}
 
 // k generations per launch where a kernel exists for the block size, else smaller blocks.
 // With wrap_rows = 0 the k rows next to each open edge are a ghost zone: their contents after a
@@ -400,7 +432,8 @@ extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uin
             if (chain_ok) {
                 if (step != prev_step) {   // new geometry: start a new chain behind everything queued so far
                     CGL_CUDA(cudaMemsetAsync(token_buf, 0, (size_t)token_cap * 4, st));
-                    chained = 0;
+                    chained = g_fault_next_chain ? 1000u : 0u;      // test hook: tokens that can never arrive
+                    g_fault_next_chain = 0;
                 }
                 chain = ChainCtx{token_buf, chained, token_cap};
             }

@@ -39,6 +39,24 @@ typedef void *cgl_stream_t;
 int cgl_abi_version(void);
 const char *cgl_last_error(void);
 
+/* ---- device-side waits never hang and never compute on stale data ---------------------------
+ * Several kernels wait on the device for a token written by another CTA, launch or GPU (chained env steps,
+ * chained life strips, the halo exchange).  Every such wait is bounded by a wall-clock deadline
+ * (cgl_set_wait_timeout_ms, default 2000 ms, per process; applied to the current device at once and to other
+ * devices at their next cgl_alarm_words call).  A waiter that gives up writes nothing that depends on the
+ * missing data, does not publish its own token, and stores 1 into its ALARM WORD: host-mapped pinned
+ * int32[CGL_ALARM_WORDS] owned by the library.  cgl_alarm_words returns the host pointer (and installs the
+ * words on the current device); the host may read them at any time without synchronising and clears them by
+ * writing 0.  Index: 0 = an action / toggle index outside [0, side*side] was ignored (the reference raises
+ * ValueError at toggle time, CGL/CGL.py:327-328), 1 = chained env step token timeout, 2 = life-mode strip
+ * token timeout, 3 = halo exchange timeout (a ring neighbour never delivered). */
+#define CGL_ALARM_WORDS 4
+int cgl_alarm_words(int **host_words_out);
+int cgl_set_wait_timeout_ms(uint32_t ms);
+/* Test hook: which = 1 makes the next chained cgl_life_run wait for strip tokens that never arrive (exercises the
+ * bounded wait + alarm path; tests only). */
+int cgl_test_fault(int which);
+
 /* Number of CUDA devices / name + SM count of `device` (replaces the device banner query,
  * CGL/CGL.py:120-140).  name_out may be NULL. */
 int cgl_device_count(int *count_out);
@@ -167,6 +185,24 @@ int cgl_toggle_rule(uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, ui
 /* stable = alive ? spawn : 0, then zeros -> empty (CGL_action+/CGL.py:122-126). */
 int cgl_init_stable_rule(const uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_t side,
                          int spawn, int empty, cgl_stream_t stream);
+
+/* ---- one environment, one launch: the body of the reference's training loop -------------------
+ * CGL/main.py:64-72 per iteration: toggle_state(action) (CGL/CGL.py:322-328) -> step() (:247-252: two H2D copies,
+ * kernel `run` :147-181, two D2H copies :203-208) -> get_stable(shallow) (:281-285) -> reward() (:255-256).
+ * cgl_sim_step does all of it for ONE environment of any side <= cgl_sim_step_max_side() in ONE kernel:
+ *   action        index in [0, side*side) toggled before the step, or side*side = none; passed BY VALUE, so
+ *                 nothing the host may rewrite later is read by the kernel
+ *   dead_rule / empty / empty_min / masked_toggle   as in cgl_env_step_rule (0, 0, 0, 0 = the base env)
+ *   obs_mirror    NULL, or int8[side*side] the kernel ALSO stores the new stability plane to -- the caller's
+ *                 pinned host-mapped observation buffer (no device-to-host copy)
+ *   result        NULL, or int32[4] (device or pinned host-mapped): [0] = reward, [1] = live cells, then -- after
+ *                 system-scope fences, so mirror and result are complete when it shows -- [2] = seq.  The host
+ *                 polls [2] instead of synchronising the stream.
+ * world_in / world_out / stable are the resident device planes as in cgl_env_step. */
+int cgl_sim_step(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev, uint32_t side,
+                 int32_t action, int spawn, int stable_max, int dead_rule, int empty, int empty_min,
+                 int masked_toggle, int8_t *obs_mirror, int32_t *result, uint32_t seq, cgl_stream_t stream);
+uint32_t cgl_sim_step_max_side(void);
 
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
