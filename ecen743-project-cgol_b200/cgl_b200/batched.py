@@ -89,12 +89,17 @@ class BatchedSim:
             self._reward = torch.zeros(B, dtype=torch.int32, device=self.device)
             self._alive = torch.zeros(B, dtype=torch.int32, device=self.device)   # uint32 bits
             self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            # per-env tokens of the chained fused step (cgl_env_step_chained): token[e] = id of the plane
-            # that holds env e's latest world (1 = first plane, 2 = second); _token_plane = the plane
-            # (data_ptr) all tokens currently name, None = stale (set again before the next chained step)
+            # Per-env tokens of the chained fused step (include/cgl_b200.h, chain_mode).  Default: SEQUENCE
+            # NUMBERS -- token[e] = number of chained steps env e has completed, `_seq` is the host counter the
+            # library reads `want` from.  A step issued under CUDA stream capture switches the batch to PLANE IDS
+            # for good (token[e] = id of the plane holding env e's world: 1 = first plane, 2 = second), because
+            # only those replay.  `_tok` records what the tokens currently hold so that they are re-initialised
+            # (one fill) when the mode changes or a non-chained op swapped the planes.
             self._tokens = torch.zeros(B, dtype=torch.int32, device=self.device) if self.fused else None
             self._plane_id = {self._wa.data_ptr(): 1, self._wb.data_ptr(): 2}
-            self._token_plane = None
+            self._seq = ctypes.c_uint32(0)
+            self._chain_ids = False
+            self._tok = None
             self._step_args = {}
             # Chaining pays when a launch is only a few waves of CTAs deep (its tail is a large share of
             # it): measured on B200 +9 % at 4096 CTAs (C2), +30 % at 2048 CTAs, +46 % at 1024 CTAs (graph
@@ -208,41 +213,33 @@ class BatchedSim:
         s_in = self.stable.data_ptr()
         s_out = s_in if obs_out is None else obs_out.data_ptr()
         r_ptr = self._reward.data_ptr() if reward_out is None else reward_out.data_ptr()
-        key = (src, a_ptr, want_alive, s_in, s_out, r_ptr)
+        mode = native.CHAIN_NONE
+        if self.chained:
+            if not self._chain_ids and torch.cuda.is_current_stream_capturing():
+                self._chain_ids = True                      # plane ids from now on: only those replay
+            mode = native.CHAIN_IDS if self._chain_ids else native.CHAIN_SEQ
+        key = (src, a_ptr, want_alive, s_in, s_out, r_ptr, mode)
         args = self._step_args.get(key)
-        if args is None:                                    # ctypes argument tuples are built once per buffer set
-            V = ctypes.c_void_p
-            dst = self._wb.data_ptr()
-            io = s_out != s_in or self._ext
-            args = [V(src), V(dst), V(s_in)]
-            if io:
-                args.append(V(s_out))
-            args += [self.n_envs, self.side, V(a_ptr), self.spawn, self.stable_max]
-            if self._ext:
-                args += [DEAD_RULES[self.dead_rule], self.empty, self.empty_min, int(self.masked_toggle)]
-            args += [V(r_ptr), V(self._alive.data_ptr()) if want_alive else None, V(self._err.data_ptr())]
-            if self.chained:
-                args += [V(self._tokens.data_ptr()), self._plane_id[src], self._plane_id[dst]]
-            elif io:
-                args += [None, 0, 0]
-            fn = (self._lib.cgl_env_step_rule if self._ext else self._lib.cgl_env_step_io if io else
-                  self._lib.cgl_env_step_chained if self.chained else self._lib.cgl_env_step)
+        if args is None:                                    # the argument struct is built once per buffer set
+            args = self._make_args(src, self._wb.data_ptr(), s_in, s_out, a_ptr, r_ptr, want_alive, mode)
             n_launch = self._lib.cgl_env_step_launches(self.side, int(actions is not None))
             if s_out != s_in and not self.fused:
                 n_launch += 1                               # the plane copy of the generic path
-            args = (tuple(args), dst, n_launch, fn)
+            args = (args, ctypes.byref(args), n_launch, self._wb.data_ptr())
             if len(self._step_args) > 4096:
                 self._step_args.clear()
             self._step_args[key] = args
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
-        if self.chained:            # per-env dependency between consecutive launches (see the C header)
-            if self._token_plane != src:            # first chained step, or a non-chained op swapped the planes
-                self._tokens.fill_(self._plane_id[src])
-            self._token_plane = args[1]
-        rc = args[3](*args[0], self._stream())
+        if mode:                    # per-env dependency between consecutive launches (see the C header)
+            self._sync_tokens(mode, src)
+        rc = self._lib.cgl_env_step_ex(args[1], self._stream())
         if rc:
-            native.check(rc, "cgl_env_step")
+            native.check(rc, "cgl_env_step_ex")
+        if mode == native.CHAIN_IDS:
+            self._tok = args[3]                             # the tokens now name the plane just written
+        elif mode:
+            self._tok = -self._seq.value - 1                # (negative: cannot collide with a plane address)
         self._wa, self._wb = self._wb, self._wa
         if obs_out is not None:
             self.stable = obs_out.view(self.n_envs, self.size)
@@ -250,6 +247,32 @@ class BatchedSim:
         self.launches += args[2]
         done = self._done[self.max_steps is not None and self.count >= self.max_steps]
         return self.stable, (self._reward if reward_out is None else reward_out), done
+
+    def _make_args(self, src, dst, s_in, s_out, a_ptr, r_ptr, want_alive, mode) -> "native.EnvStepArgs":
+        a = native.EnvStepArgs()
+        a.world_in, a.world_out, a.stable_in, a.stable_out = src, dst, s_in, s_out
+        a.n_envs, a.side, a.spawn, a.stable_max = self.n_envs, self.side, self.spawn, self.stable_max
+        a.dead_rule, a.empty, a.empty_min = DEAD_RULES[self.dead_rule], self.empty, self.empty_min
+        a.masked_toggle = int(self.masked_toggle)
+        a.actions, a.reward_out = a_ptr or None, r_ptr or None
+        a.alive_out = self._alive.data_ptr() if want_alive else None
+        a.err_flag = self._err.data_ptr()
+        a.chain_mode = mode
+        if mode:
+            a.token = self._tokens.data_ptr()
+            if mode == native.CHAIN_IDS:
+                a.want, a.publish = self._plane_id[src], self._plane_id[dst]
+            else:
+                a.seq_counter = ctypes.pointer(self._seq)
+        return a
+
+    def _sync_tokens(self, mode, src) -> None:
+        """Make the tokens hold what the next chained step waits for (a fill only when something changed that)."""
+        want = src if mode == native.CHAIN_IDS else -self._seq.value - 1
+        if self._tok != want:
+            self._tokens.fill_(self._plane_id[src] if mode == native.CHAIN_IDS else
+                               self._seq.value - (1 << 32 if self._seq.value >= 1 << 31 else 0))
+            self._tok = want
 
     def run(self, max_steps: int, until_fixed: bool = False, want_alive: bool = False):
         """`max_steps` plain steps (no actions) for every env in ONE launch, the environments resident in
@@ -464,3 +487,93 @@ class BatchedSim:
         if rc:
             native.check(rc, "cgl_stream_wait")
 
+
+class StepSequence:
+    """K env steps enqueued by ONE C-ABI call (`cgl_env_step_seq`): step i steps sims[i % R] with actions[i % A].
+
+    The launch loop runs in C, so the host cost of a step is one kernel launch; consecutive launches overlap
+    through programmatic dependent launch (and per-env chaining where the sims use it) exactly as with step().
+    All sims must share n_envs / side / constants and live on one device; actions: int32 [A, n_envs] on that
+    device or None.  Rewards go to each sim's own reward buffer (sim._reward)."""
+
+    def __init__(self, sims, actions=None):
+        s0 = sims[0]
+        for s in sims:
+            if (s.n_envs, s.side, s.spawn, s.stable_max, s.device) != (s0.n_envs, s0.side, s0.spawn, s0.stable_max, s0.device):
+                raise ValueError("all sims of a StepSequence must have the same shape, constants and device")
+            if s._ext:
+                raise native.CglNativeError("StepSequence implements the base env only")
+        if actions is not None and (actions.dtype != torch.int32 or actions.device != s0.device or actions.dim() != 2
+                                    or actions.shape[1] != s0.n_envs or not actions.is_contiguous()):
+            raise TypeError("actions must be a contiguous int32 tensor [A, n_envs] on the sims' device")
+        self.sims, self.actions = list(sims), actions
+        self._lib = s0._lib
+        self._cache = {}
+
+    def _descs(self):
+        sims, R = self.sims, len(self.sims)
+        A = 1 if self.actions is None else self.actions.shape[0]
+        modes = tuple(0 if not s.chained else native.CHAIN_IDS if s._chain_ids else native.CHAIN_SEQ for s in sims)
+        key = tuple(s._wa.data_ptr() for s in sims) + tuple(s.stable.data_ptr() for s in sims) + modes
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        n = 2 * R * A // int(np.gcd(2 * R, A))              # one full cycle: planes and actions back in place
+        descs = (native.EnvStepArgs * n)()
+        planes = [[s._wa.data_ptr(), s._wb.data_ptr()] for s in sims]
+        row = 0 if self.actions is None else self.actions.stride(0) * 4
+        for i in range(n):
+            j, s = i % R, sims[i % R]
+            src, dst = planes[j]
+            a_ptr = 0 if self.actions is None else self.actions.data_ptr() + (i % A) * row
+            descs[i] = s._make_args(src, dst, s.stable.data_ptr(), s.stable.data_ptr(), a_ptr, s._reward.data_ptr(),
+                                    False, modes[j])
+            planes[j] = [dst, src]
+        if len(self._cache) > 64:
+            self._cache.clear()
+        self._cache[key] = (descs, n, modes)
+        return descs, n, modes
+
+    def run(self, n_steps: int) -> None:
+        """Enqueue n_steps steps (step i: sims[i % R], actions[i % A]) on the current stream.  Returns at once."""
+        self.prepare(n_steps)()
+
+    def prepare(self, n_steps: int):
+        """Everything run() can do ahead of time, done now; returns a function that issues the n_steps launches: a
+        cache lookup for the descriptor cycle of the current plane orientation, ONE C-ABI call, then the plane
+        bookkeeping.  A benchmark calls prepare() outside its timed region so that the region starts with the first
+        launch, not with Python.  The function may be called any number of times (planes may flip in between)."""
+        sims = self.sims
+        s0 = sims[0]
+        for s in sims:
+            if s.chained and not s._chain_ids and torch.cuda.is_current_stream_capturing():
+                s._chain_ids = True
+        if torch.cuda.current_device() != s0.device.index:
+            torch.cuda.set_device(s0.device)
+        stream = s0._stream()
+        fn, alarm = self._lib.cgl_env_step_seq, s0._alarm
+        self._descs()                                       # warm the cache for the current orientation
+
+        def issue():
+            if alarm[1]:
+                native.check_alarm()
+            descs, n, modes = self._descs()
+            for s, mode in zip(sims, modes):
+                if mode == native.CHAIN_IDS or s._tok is None:
+                    s._sync_tokens(mode, s._wa.data_ptr())
+            rc = fn(descs, n, n_steps, 0, stream)
+            if rc:
+                native.check(rc, "cgl_env_step_seq")
+            self._after(n_steps, modes)
+        return issue
+
+    def _after(self, n_steps, modes):
+        sims, R = self.sims, len(self.sims)
+        for j, s in enumerate(sims):
+            c = max(0, (n_steps - j + R - 1) // R)                 # steps that fell on sim j
+            if c & 1:
+                s._wa, s._wb = s._wb, s._wa
+            if c and modes[j]:
+                s._tok = s._wa.data_ptr() if modes[j] == native.CHAIN_IDS else -s._seq.value - 1
+            s.count += c
+            s.launches += c

@@ -74,6 +74,28 @@ SIGNATURES = {
     "cgl_dev_memset": (_i, [_vp, _i, _u64, _vp]),
 }
 
+class EnvStepArgs(ctypes.Structure):
+    """cgl_env_step_args_t (include/cgl_b200.h)."""
+    _fields_ = [("world_in", _vp), ("world_out", _vp), ("stable_in", _vp), ("stable_out", _vp), ("n_envs", _u64),
+                ("side", _u32), ("spawn", ctypes.c_int32), ("stable_max", ctypes.c_int32), ("dead_rule", ctypes.c_int32),
+                ("empty", ctypes.c_int32), ("empty_min", ctypes.c_int32), ("masked_toggle", ctypes.c_int32),
+                ("actions", _vp), ("reward_out", _vp), ("alive_out", _vp), ("err_flag", _vp), ("token", _vp),
+                ("want", _u32), ("publish", _u32), ("chain_mode", _u32), ("seq_counter", ctypes.POINTER(_u32))]
+
+
+CHAIN_NONE, CHAIN_IDS, CHAIN_SEQ = 0, 1, 2
+SIGNATURES["cgl_env_step_ex"] = (_i, [ctypes.POINTER(EnvStepArgs), _vp])
+SIGNATURES["cgl_env_step_seq"] = (_i, [ctypes.POINTER(EnvStepArgs), _u32, _u64, _u64, _vp])
+
+POLICY_FN = ctypes.CFUNCTYPE(None, _vp, _u32, _u64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32))
+SIGNATURES["cgl_rollout_create"] = (_i, [ctypes.POINTER(_vp), _u32, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                         ctypes.POINTER(_vp), _u64, _u32, _i, _i, ctypes.POINTER(_vp)])
+SIGNATURES["cgl_rollout_buffers"] = (_i, [_vp, _u32, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                          ctypes.POINTER(ctypes.POINTER(ctypes.c_int32))])
+SIGNATURES["cgl_rollout_run"] = (_i, [_vp, _u64, _vp, _vp])
+SIGNATURES["cgl_rollout_parity"] = (_i, [_vp, _u32, _u32])
+SIGNATURES["cgl_rollout_destroy"] = (_i, [_vp])
+
 _lib = None
 
 

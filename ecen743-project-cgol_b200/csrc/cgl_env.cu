@@ -102,7 +102,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
                       const int32_t *__restrict__ actions, uint32_t spawn4, uint32_t max4,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out,
                       int *__restrict__ err_flag, uint32_t *__restrict__ epoch, uint32_t want, uint32_t publish,
-                      uint32_t min4, uint32_t empty4, int masked)
+                      uint32_t min4, uint32_t empty4, int masked, int seq_tokens)
 {
     constexpr bool EXT = RULE >= 0;
     using C = EnvCfg<S>;
@@ -139,23 +139,36 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         // dispatched in env order.  The token load is issued first and the mask tables are filled in
         // its shadow.
         //
-        // Two plane ids are enough BECAUSE this CTA allows its dependents to launch only after its own wait
-        // has succeeded: launch n+2 can start only when every CTA of launch n+1 has triggered, i.e. has seen
-        // the token of launch n for its env, i.e. when launch n has completely finished.  So at most two
-        // consecutive chained launches are ever in flight and a token value cannot be mistaken for the one
-        // two launches back (which it could if the trigger came first -- with small batches three grids fit
-        // on the GPU at once).
+        // Token values.  seq_tokens: want / publish are consecutive per-env SEQUENCE NUMBERS (32 bits, compared
+        // for equality): a token value then names exactly one launch, any number of launches may be in flight,
+        // and the CTA triggers its dependents at entry.  Otherwise they are two PLANE IDS that alternate (a
+        // captured CUDA graph replays, which baked-in sequence numbers cannot): two ids are enough ONLY IF a CTA
+        // allows its dependents to launch once it has SEEN its token -- launch n+2 can then start only when
+        // every CTA of launch n+1 has seen the token of launch n, i.e. when launch n has completely finished,
+        // so at most two consecutive launches are in flight and an id cannot be mistaken for the same id two
+        // launches back (with the trigger at entry and small batches three grids fit on the GPU at once: the
+        // round-1 bug).  The trigger sits on the launch-to-launch critical path (the dependent grid fills the
+        // slots this grid's last, partial wave leaves free; measured per C2 step: trigger behind the barrier
+        // 26.5 us, decided per thread from a relaxed load of the token 25.7 us, at entry 24.9 us).  A CTA counts
+        // as triggered as soon as ANY of its threads has executed the trigger (measured: letting the idle warps
+        // of a partly filled CTA trigger early brings the hazard back), so in id mode CTAs that hold several
+        // envs (side <= 64: one warp each) trigger behind the barrier that collects all their tokens.
         //
         // The wait is bounded (g_wait_ns, cgl_set_wait_timeout_ms).  A token that never arrives (caller bug,
         // a predecessor that was never launched) sets bit 1 of the error flag, raises the alarm word and
         // SKIPS the env: no plane is written and no token published, so nothing is computed from stale
         // planes and every later chained step of that env fails the same way (fast: see wait_expired).
-        uint32_t v = want;
+        if (seq_tokens) cudaTriggerProgrammaticLaunchCompletion();
+        uint32_t v = want, v_seen = want;
+        if (C::EPC == 1 && active && !seq_tokens)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v_seen) : "l"(epoch + e) : "memory");
         if (t == 0 && active) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
         for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
             const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
             tables[i] = (i & 32) ? (m & spawn4) : m;
         }
+        const bool seen = seq_tokens || (C::EPC == 1 && v_seen == want);     // seen: already triggered
+        if (seen && !seq_tokens) cudaTriggerProgrammaticLaunchCompletion();
         if (t == 0) {
             if (active && v != want) {
                 const unsigned long long t0 = globaltimer_ns();
@@ -171,7 +184,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             red[2] = (v == want);
         }
         __syncthreads();
-        cudaTriggerProgrammaticLaunchCompletion();
+        if (!seen) cudaTriggerProgrammaticLaunchCompletion();
         active = active && red[2] != 0;
     }
 
@@ -347,7 +360,9 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
 
 CGL_DEFINE_TU_HOOKS(env)
 
-// CGL_ENV_PDL=0 turns programmatic dependent launch off (tuning / debugging).
+// CGL_ENV_PDL=0 turns programmatic dependent launch off (tuning / debugging); cgl_rollout.cu suppresses it while
+// it captures its copy -> step graphs.
+int g_pdl_suppress = 0;
 static bool pdl_enabled()
 {
     static int v = -1;
@@ -355,17 +370,14 @@ static bool pdl_enabled()
         const char *e = getenv("CGL_ENV_PDL");
         v = (e && e[0] == '0') ? 0 : 1;
     }
-    return v != 0;
+    return v != 0 && !g_pdl_suppress;
 }
 
 template <int S>
-static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
-                            const int32_t *actions, int spawn, int stable_max, int32_t *reward,
-                            uint32_t *alive, int *err, cudaStream_t st, uint32_t *epoch = nullptr, uint32_t want = 0,
-                            uint32_t publish = 0, int8_t *stable_out = nullptr, const RuleArgs *ext = nullptr)
+static int launch_env_fused(const cgl_env_step_args_t &a, cudaStream_t st)
 {
     using C = EnvCfg<S>;
-    const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
+    const unsigned grid = (unsigned)((a.n_envs + C::EPC - 1) / C::EPC);
     static int pad = -1;                        // tuning knob: extra dynamic smem limits CTAs/SM
     static PerDeviceOnce once;
     if (pad < 0) {
@@ -394,26 +406,27 @@ static int launch_env_fused(const uint32_t *win, uint32_t *wout, int8_t *stable,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    const uint32_t n32 = (uint32_t)n_envs, sp4 = rep4(spawn), mx4 = rep4(stable_max);
-    if (ext != nullptr) {               // fork variants: separate in/out planes (they may alias), one kernel per rule
-        int8_t *so = stable_out != nullptr ? stable_out : stable;
-        const uint32_t mn4 = rep4(ext->empty_min), em4 = rep4(ext->empty);
-        if (ext->rule == CGL_DEAD_DECAY)
-            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_DECAY>, win, wout, stable, so, n32,
-                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
-        else if (ext->rule == CGL_DEAD_SAT)
-            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_SAT>, win, wout, stable, so, n32,
-                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
-        else
-            CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, CGL_DEAD_ZERO>, win, wout, stable, so, n32,
-                                        actions, sp4, mx4, reward, alive, err, epoch, want, publish, mn4, em4, ext->masked));
-    } else if (stable_out != nullptr && stable_out != stable) {
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, true, -1>, win, wout, stable, stable_out, n32, actions,
-                                    sp4, mx4, reward, alive, err, epoch, want, publish, 0u, 0u, 0));
+    const uint32_t n32 = (uint32_t)a.n_envs, sp4 = rep4(a.spawn), mx4 = rep4(a.stable_max);
+    const uint32_t mn4 = rep4(a.empty_min), em4 = rep4(a.empty);
+    const uint32_t *win = a.world_in_dev;
+    uint32_t *wout = a.world_out_dev;
+    int8_t *sin = const_cast<int8_t *>(a.stable_in_dev), *sout = a.stable_out_dev;
+    uint32_t *tok = a.chain_mode != CGL_CHAIN_NONE ? a.token_dev : nullptr;
+    const int seq = a.chain_mode == CGL_CHAIN_SEQ, masked = a.masked_toggle != 0;
+#define CGL_LAUNCH(IO, RULE)                                                                                        \
+    CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, IO, RULE>, win, wout, sin, sout, n32, a.actions_dev, \
+                                sp4, mx4, a.reward_out_dev, a.alive_out_dev, a.err_flag_dev, tok, a.want, a.publish, \
+                                mn4, em4, masked, seq))
+    if (a.dead_rule != CGL_DEAD_ZERO || masked) {   // fork variants: one kernel per rule, in/out planes may alias
+        if (a.dead_rule == CGL_DEAD_DECAY) CGL_LAUNCH(true, CGL_DEAD_DECAY);
+        else if (a.dead_rule == CGL_DEAD_SAT) CGL_LAUNCH(true, CGL_DEAD_SAT);
+        else CGL_LAUNCH(true, CGL_DEAD_ZERO);
+    } else if (sout != sin) {
+        CGL_LAUNCH(true, -1);
     } else {
-        CGL_CUDA(cudaLaunchKernelEx(&cfg, env_step_fused_kernel<S, false, -1>, win, wout, stable, stable, n32, actions,
-                                    sp4, mx4, reward, alive, err, epoch, want, publish, 0u, 0u, 0));
+        CGL_LAUNCH(false, -1);
     }
+#undef CGL_LAUNCH
     return 0;
 }
 
@@ -735,67 +748,115 @@ static int env_tma_threads()
     return v;
 }
 
+// The one implementation behind every env-step entry point (see include/cgl_b200.h, cgl_env_step_ex).
+extern "C" int cgl_env_step_ex(const cgl_env_step_args_t *args, cgl_stream_t stream)
+{
+    CGL_REQUIRE(args, CGL_E_BADARG, "cgl_env_step_ex: null");
+    cgl_env_step_args_t a = *args;
+    CGL_REQUIRE(a.world_in_dev && a.world_out_dev && a.stable_in_dev && a.n_envs && a.side, CGL_E_BADARG,
+                "cgl_env_step: bad argument");
+    CGL_REQUIRE(a.world_in_dev != a.world_out_dev, CGL_E_BADARG, "cgl_env_step: world_in and world_out must not alias");
+    CGL_REQUIRE(a.n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step: n_envs too large");
+    CGL_REQUIRE(a.dead_rule >= CGL_DEAD_ZERO && a.dead_rule <= CGL_DEAD_SAT, CGL_E_BADARG,
+                "cgl_env_step: dead_rule must be 0 (zero), 1 (decay) or 2 (saturate)");
+    CGL_REQUIRE(a.empty >= -128 && a.empty <= 127 && a.empty_min >= -128 && a.empty_min <= 127, CGL_E_BADARG,
+                "cgl_env_step: empty / empty_min must fit int8");
+    CGL_REQUIRE(a.chain_mode <= CGL_CHAIN_SEQ && (a.chain_mode == CGL_CHAIN_NONE || a.token_dev), CGL_E_BADARG,
+                "cgl_env_step: chain_mode must be 0..2 and needs token_dev");
+    if (a.stable_out_dev == nullptr) a.stable_out_dev = const_cast<int8_t *>(a.stable_in_dev);
+    if (a.chain_mode == CGL_CHAIN_NONE) a.token_dev = nullptr;
+    const bool fused = cgl_env_step_is_fused(a.side);
+    CGL_REQUIRE(fused || a.chain_mode == CGL_CHAIN_NONE, CGL_E_BADARG,
+                "cgl_env_step: chained steps need a fused side (multiple of 32, 32..256)");
+    if (a.chain_mode == CGL_CHAIN_SEQ && a.seq_counter_host != nullptr) {
+        a.want = *a.seq_counter_host;               // consecutive sequence numbers, kept by the caller's counter
+        a.publish = a.want + 1;
+    }
+    cudaStream_t st = as_stream(stream);
+    const bool ext = a.dead_rule != CGL_DEAD_ZERO || a.masked_toggle;
+    int rc = -100;
+    if (!ext && a.stable_out_dev == a.stable_in_dev && a.chain_mode == CGL_CHAIN_NONE && env_impl_is_tma() &&
+        (a.side == 32 || a.side == 64 || a.side == 128))
+        rc = cgl_env_step_tma(a.world_in_dev, a.world_out_dev, a.stable_out_dev, a.n_envs, a.side, a.actions_dev, a.spawn,
+                              a.stable_max, a.reward_out_dev, a.alive_out_dev, a.err_flag_dev, stream, env_tma_threads());
+    if (rc == -100 && fused) {
+        switch (a.side) {
+        case 32: rc = launch_env_fused<32>(a, st); break;
+        case 64: rc = launch_env_fused<64>(a, st); break;
+        case 96: rc = launch_env_fused<96>(a, st); break;
+        case 128: rc = launch_env_fused<128>(a, st); break;
+        case 160: rc = launch_env_fused<160>(a, st); break;
+        case 192: rc = launch_env_fused<192>(a, st); break;
+        case 224: rc = launch_env_fused<224>(a, st); break;
+        case 256: rc = launch_env_fused<256>(a, st); break;
+        }
+    }
+    if (rc == -100) {
+        // generic sides: (plane copy) -> toggle -> generation -> stability, all in place on stable_out
+        const uint32_t W = cgl_words_per_row(a.side);
+        const uint64_t cells = a.n_envs * a.side * a.side;
+        if (a.stable_in_dev != a.stable_out_dev)
+            CGL_CUDA(cudaMemcpyAsync(a.stable_out_dev, a.stable_in_dev, cells, cudaMemcpyDeviceToDevice, st));
+        if (a.actions_dev != nullptr &&
+            (rc = cgl_toggle_rule(a.world_in_dev, a.stable_out_dev, a.n_envs, a.side, a.actions_dev, 1, a.spawn,
+                                  a.masked_toggle, a.err_flag_dev, stream)))
+            return rc;
+        if ((rc = cgl_life_step(a.world_in_dev, a.world_out_dev, a.n_envs, a.side, a.side, 1, a.alive_out_dev, stream)))
+            return rc;
+        if (a.reward_out_dev != nullptr) CGL_CUDA(cudaMemsetAsync(a.reward_out_dev, 0, a.n_envs * sizeof(int32_t), st));
+        stable_generic_kernel<<<grid_for(cells, 256), 256, 0, st>>>(
+            a.world_in_dev, a.world_out_dev, a.stable_out_dev, a.n_envs, a.side, W, (int8_t)a.spawn, (int8_t)a.stable_max,
+            a.reward_out_dev, a.dead_rule, (int8_t)a.empty, (int8_t)a.empty_min);
+        CGL_LAUNCH_CHECK();
+        rc = 0;
+    }
+    if (rc == 0 && a.chain_mode == CGL_CHAIN_SEQ && a.seq_counter_host != nullptr) ++*a.seq_counter_host;
+    return rc;
+}
+
+static cgl_env_step_args_t base_args(uint32_t *win, uint32_t *wout, const int8_t *sin, int8_t *sout, uint64_t n_envs,
+                                     uint32_t side, const int32_t *actions, int spawn, int stable_max, int32_t *reward,
+                                     uint32_t *alive, int *err)
+{
+    cgl_env_step_args_t a = {};
+    a.world_in_dev = win; a.world_out_dev = wout; a.stable_in_dev = sin; a.stable_out_dev = sout;
+    a.n_envs = n_envs; a.side = side; a.actions_dev = actions; a.spawn = spawn; a.stable_max = stable_max;
+    a.reward_out_dev = reward; a.alive_out_dev = alive; a.err_flag_dev = err;
+    return a;
+}
+
 extern "C" int cgl_env_step(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs,
                             uint32_t side, const int32_t *actions, int spawn, int stable_max,
                             int32_t *reward, uint32_t *alive, int *err, cgl_stream_t stream)
 {
-    CGL_REQUIRE(win && wout && stable && n_envs && side, CGL_E_BADARG, "cgl_env_step: bad argument");
-    CGL_REQUIRE(win != wout, CGL_E_BADARG, "cgl_env_step: world_in and world_out must not alias");
-    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step: n_envs too large");
-    cudaStream_t st = as_stream(stream);
-    if (env_impl_is_tma() && (side == 32 || side == 64 || side == 128)) {
-        const int rc = cgl_env_step_tma(win, wout, stable, n_envs, side, actions, spawn, stable_max, reward,
-                                        alive, err, stream, env_tma_threads());
-        if (rc != -100) return rc;
-    }
-    if (cgl_env_step_is_fused(side)) {
-#define CGL_CASE(S)                                                                               \
-    case S:                                                                                       \
-        return launch_env_fused<S>(win, wout, stable, n_envs, actions, spawn, stable_max, reward, \
-                                   alive, err, st)
-        switch (side) {
-            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
-            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
-        }
-#undef CGL_CASE
-    }
-    // generic: toggle -> generation -> stability
-    const uint32_t W = cgl_words_per_row(side);
-    if (actions != nullptr) {
-        int rc = cgl_toggle(win, stable, n_envs, side, actions, 1, spawn, err, stream);
-        if (rc) return rc;
-    }
-    int rc = cgl_life_step(win, wout, n_envs, side, side, 1, alive, stream);
-    if (rc) return rc;
-    if (reward != nullptr) CGL_CUDA(cudaMemsetAsync(reward, 0, n_envs * sizeof(int32_t), st));
-    const uint64_t total = n_envs * side * side;
-    stable_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-        win, wout, stable, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward, CGL_DEAD_ZERO, 0, 0);
-    CGL_LAUNCH_CHECK();
-    return 0;
+    const cgl_env_step_args_t a = base_args(win, wout, stable, stable, n_envs, side, actions, spawn, stable_max, reward,
+                                            alive, err);
+    return cgl_env_step_ex(&a, stream);
 }
 
-// Chained form of cgl_env_step for the fused sides: see include/cgl_b200.h.
+// Chained form of cgl_env_step for the fused sides (plane ids: replayable): see include/cgl_b200.h.
 extern "C" int cgl_env_step_chained(uint32_t *win, uint32_t *wout, int8_t *stable, uint64_t n_envs, uint32_t side,
                                     const int32_t *actions, int spawn, int stable_max, int32_t *reward,
                                     uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want,
                                     uint32_t publish, cgl_stream_t stream)
 {
-    CGL_REQUIRE(win && wout && stable && n_envs && side && epoch_flags && win != wout, CGL_E_BADARG,
-                "cgl_env_step_chained: bad argument");
-    CGL_REQUIRE(cgl_env_step_is_fused(side) && n_envs < (1ull << 31), CGL_E_BADARG,
-                "cgl_env_step_chained: side must be a fused side (multiple of 32, 32..256)");
-    cudaStream_t st = as_stream(stream);
-#define CGL_CASE(S)                                                                               \
-    case S:                                                                                       \
-        return launch_env_fused<S>(win, wout, stable, n_envs, actions, spawn, stable_max, reward, \
-                                   alive, err, st, epoch_flags, want, publish)
-    switch (side) {
-        CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
-        CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
+    CGL_REQUIRE(epoch_flags, CGL_E_BADARG, "cgl_env_step_chained: bad argument");
+    cgl_env_step_args_t a = base_args(win, wout, stable, stable, n_envs, side, actions, spawn, stable_max, reward, alive, err);
+    a.token_dev = epoch_flags; a.want = want; a.publish = publish; a.chain_mode = CGL_CHAIN_IDS;
+    return cgl_env_step_ex(&a, stream);
+}
+
+// A whole sequence of env steps enqueued by ONE call (see include/cgl_b200.h): the launch loop runs in C, so the
+// host side of a step is one cudaLaunchKernelEx (~2 us) instead of a trip through the binding per step.
+extern "C" int cgl_env_step_seq(const cgl_env_step_args_t *steps, uint32_t n_descs, uint64_t n_steps, uint64_t first,
+                                cgl_stream_t stream)
+{
+    CGL_REQUIRE(steps && n_descs, CGL_E_BADARG, "cgl_env_step_seq: bad argument");
+    for (uint64_t i = 0; i < n_steps; ++i) {
+        const int rc = cgl_env_step_ex(&steps[(first + i) % n_descs], stream);
+        if (rc) return rc;
     }
-#undef CGL_CASE
-    return CGL_E_BADARG;
+    return 0;
 }
 
 // Out-of-place form: the new stability plane goes to `stable_out` (see include/cgl_b200.h).
@@ -804,26 +865,12 @@ extern "C" int cgl_env_step_io(uint32_t *win, uint32_t *wout, const int8_t *stab
                                int32_t *reward, uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want,
                                uint32_t publish, cgl_stream_t stream)
 {
-    CGL_REQUIRE(win && wout && stable_in && stable_out && n_envs && side && win != wout, CGL_E_BADARG,
-                "cgl_env_step_io: bad argument");
-    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step_io: n_envs too large");
-    cudaStream_t st = as_stream(stream);
-    if (cgl_env_step_is_fused(side)) {
-#define CGL_CASE(S)                                                                                     \
-    case S:                                                                                             \
-        return launch_env_fused<S>(win, wout, const_cast<int8_t *>(stable_in), n_envs, actions, spawn,  \
-                                   stable_max, reward, alive, err, st, epoch_flags, want, publish, stable_out)
-        switch (side) {
-            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
-            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
-        }
-#undef CGL_CASE
-    }
-    CGL_REQUIRE(epoch_flags == nullptr, CGL_E_BADARG, "cgl_env_step_io: tokens need a fused side");
-    // generic sides: copy the plane, then the in-place three-kernel path on the copy
-    if (stable_in != stable_out)
-        CGL_CUDA(cudaMemcpyAsync(stable_out, stable_in, n_envs * side * side, cudaMemcpyDeviceToDevice, st));
-    return cgl_env_step(win, wout, stable_out, n_envs, side, actions, spawn, stable_max, reward, alive, err, stream);
+    CGL_REQUIRE(stable_out, CGL_E_BADARG, "cgl_env_step_io: bad argument");
+    cgl_env_step_args_t a = base_args(win, wout, stable_in, stable_out, n_envs, side, actions, spawn, stable_max, reward,
+                                      alive, err);
+    a.token_dev = epoch_flags; a.want = want; a.publish = publish;
+    a.chain_mode = epoch_flags ? CGL_CHAIN_IDS : CGL_CHAIN_NONE;
+    return cgl_env_step_ex(&a, stream);
 }
 
 // The CGL_action+ fork's env step: see include/cgl_b200.h.
@@ -833,42 +880,13 @@ extern "C" int cgl_env_step_rule(uint32_t *win, uint32_t *wout, const int8_t *st
                                  uint32_t *alive, int *err, uint32_t *epoch_flags, uint32_t want, uint32_t publish,
                                  cgl_stream_t stream)
 {
-    CGL_REQUIRE(win && wout && stable_in && stable_out && n_envs && side && win != wout, CGL_E_BADARG,
-                "cgl_env_step_rule: bad argument");
-    CGL_REQUIRE(n_envs < (1ull << 31), CGL_E_BADARG, "cgl_env_step_rule: n_envs too large");
-    CGL_REQUIRE(dead_rule >= CGL_DEAD_ZERO && dead_rule <= CGL_DEAD_SAT, CGL_E_BADARG,
-                "cgl_env_step_rule: dead_rule must be 0 (zero), 1 (decay) or 2 (saturate)");
-    CGL_REQUIRE(empty >= -128 && empty <= 127 && empty_min >= -128 && empty_min <= 127, CGL_E_BADARG,
-                "cgl_env_step_rule: empty / empty_min must fit int8");
-    cudaStream_t st = as_stream(stream);
-    const RuleArgs ext = {dead_rule, empty, empty_min, masked_toggle != 0};
-    if (cgl_env_step_is_fused(side)) {
-#define CGL_CASE(S)                                                                                     \
-    case S:                                                                                             \
-        return launch_env_fused<S>(win, wout, const_cast<int8_t *>(stable_in), n_envs, actions, spawn,  \
-                                   stable_max, reward, alive, err, st, epoch_flags, want, publish, stable_out, &ext)
-        switch (side) {
-            CGL_CASE(32); CGL_CASE(64); CGL_CASE(96); CGL_CASE(128);
-            CGL_CASE(160); CGL_CASE(192); CGL_CASE(224); CGL_CASE(256);
-        }
-#undef CGL_CASE
-    }
-    CGL_REQUIRE(epoch_flags == nullptr, CGL_E_BADARG, "cgl_env_step_rule: tokens need a fused side");
-    if (stable_in != stable_out)
-        CGL_CUDA(cudaMemcpyAsync(stable_out, stable_in, n_envs * side * side, cudaMemcpyDeviceToDevice, st));
-    const uint32_t W = cgl_words_per_row(side);
-    if (actions != nullptr) {
-        int rc = cgl_toggle_rule(win, stable_out, n_envs, side, actions, 1, spawn, masked_toggle, err, stream);
-        if (rc) return rc;
-    }
-    int rc = cgl_life_step(win, wout, n_envs, side, side, 1, alive, stream);
-    if (rc) return rc;
-    if (reward != nullptr) CGL_CUDA(cudaMemsetAsync(reward, 0, n_envs * sizeof(int32_t), st));
-    stable_generic_kernel<<<grid_for(n_envs * side * side, 256), 256, 0, st>>>(
-        win, wout, stable_out, n_envs, side, W, (int8_t)spawn, (int8_t)stable_max, reward, dead_rule,
-        (int8_t)empty, (int8_t)empty_min);
-    CGL_LAUNCH_CHECK();
-    return 0;
+    CGL_REQUIRE(stable_out, CGL_E_BADARG, "cgl_env_step_rule: bad argument");
+    cgl_env_step_args_t a = base_args(win, wout, stable_in, stable_out, n_envs, side, actions, spawn, stable_max, reward,
+                                      alive, err);
+    a.dead_rule = dead_rule; a.empty = empty; a.empty_min = empty_min; a.masked_toggle = masked_toggle != 0;
+    a.token_dev = epoch_flags; a.want = want; a.publish = publish;
+    a.chain_mode = epoch_flags ? CGL_CHAIN_IDS : CGL_CHAIN_NONE;
+    return cgl_env_step_ex(&a, stream);
 }
 
 extern "C" int cgl_life_step_generic(const uint32_t *in, uint32_t *out, uint64_t n_envs, uint32_t rows,

@@ -90,7 +90,7 @@ int cgl_toggle(uint32_t *world_dev, int8_t *stable_dev, uint64_t n_envs, uint32_
 /* ---- the env step: toggle (optional) -> generation -> stability -> reward ----------------
  * Replaces kernel `run` (CGL/CGL.py:147-181) + `__step_state_gpu` (:203-208) + reward()
  * (:255-256) + alive() (:259-260) for n_envs independent environments, fused in one launch on
- * the fast path (side % 32 == 0, side <= 512) and three launches otherwise.
+ * the fast path (side % 32 == 0, 32 <= side <= 256) and three launches otherwise.
  *   world_in_dev   packed world at t.  Scratch after the call (the generic path applies the
  *                  toggle in place); world_out_dev receives t+1.  Must not alias.
  *   stable_dev     updated in place.
@@ -111,12 +111,56 @@ int cgl_env_step(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable
  * CUDA graph of an even number of steps replayable.  The next launch's first CTAs then run while this
  * launch's last CTAs finish (programmatic dependent launch without the grid-wide wait).  Anything
  * else that touches the state between two chained steps is ordered by the stream as usual.  A
- * token that does not arrive within ~1 s sets bit 1 of *err_flag_dev instead of hanging. */
+ * token that does not arrive within the wait bound (cgl_set_wait_timeout_ms) sets bit 1 of *err_flag_dev and the
+ * alarm word, and the env is SKIPPED (nothing written, token not published) instead of being stepped from stale
+ * planes. */
 int cgl_env_step_chained(uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *stable_dev,
                          uint64_t n_envs, uint32_t side, const int32_t *actions_dev, int spawn,
                          int stable_max, int32_t *reward_out_dev, uint32_t *alive_out_dev,
                          int *err_flag_dev, uint32_t *token_dev, uint32_t want, uint32_t publish,
                          cgl_stream_t stream);
+
+/* ---- the general form: every env-step entry point above and below is a thin wrapper of this one ----
+ * One struct describes a step completely, so a caller (or a binding) fills it once per buffer set and passes one
+ * pointer per step.  Zero-initialise it; fields not mentioned keep the meaning they have in cgl_env_step.
+ *   stable_in_dev / stable_out_dev   read / written stability planes (out == NULL or == in: in place)
+ *   dead_rule / empty / empty_min / masked_toggle   the CGL_action+ fork's variants (all 0 = the base env)
+ *   chain_mode   how consecutive steps on one stream depend on each other (fused sides only for 1 and 2):
+ *     CGL_CHAIN_NONE  per launch (programmatic dependent launch, the whole previous grid);
+ *     CGL_CHAIN_IDS   per environment through token_dev[e], `want` / `publish` = ids of the world planes
+ *                     (see cgl_env_step_chained): a captured CUDA graph of an even number of steps replays;
+ *     CGL_CHAIN_SEQ   per environment through token_dev[e] holding SEQUENCE NUMBERS: env e waits for
+ *                     token[e] == want and publishes want + 1.  The fastest form (a CTA releases its dependents
+ *                     at entry: 24.9 vs 25.7 us per 4096 x 128^2 step), but consecutive steps must carry
+ *                     consecutive numbers, so a captured graph cannot be replayed.  If seq_counter_host is not
+ *                     NULL the library reads `want` from it and increments it after the launch (the caller keeps
+ *                     one host counter per env batch and initialises all tokens to its value). */
+#define CGL_CHAIN_NONE 0u
+#define CGL_CHAIN_IDS  1u
+#define CGL_CHAIN_SEQ  2u
+typedef struct cgl_env_step_args {
+    uint32_t *world_in_dev, *world_out_dev;
+    const int8_t *stable_in_dev;
+    int8_t *stable_out_dev;
+    uint64_t n_envs;
+    uint32_t side;
+    int32_t spawn, stable_max, dead_rule, empty, empty_min, masked_toggle;
+    const int32_t *actions_dev;       /* or NULL */
+    int32_t *reward_out_dev;          /* or NULL */
+    uint32_t *alive_out_dev;          /* or NULL */
+    int *err_flag_dev;                /* or NULL */
+    uint32_t *token_dev;              /* chain_mode 1, 2 */
+    uint32_t want, publish, chain_mode;
+    uint32_t *seq_counter_host;       /* chain_mode 2, or NULL */
+} cgl_env_step_args_t;
+int cgl_env_step_ex(const cgl_env_step_args_t *args, cgl_stream_t stream);
+
+/* A sequence of env steps enqueued by ONE call: step i (i = 0 .. n_steps-1) is cgl_env_step_ex(&steps[(first + i) %
+ * n_descs]).  A caller that rotates several env batches and ping-pong planes describes one full cycle and lets it
+ * repeat.  The launches are issued back to back from C (the host cost of a step is one kernel launch), on `stream`,
+ * asynchronously.  The descriptors must stay valid only for the duration of the call. */
+int cgl_env_step_seq(const cgl_env_step_args_t *steps, uint32_t n_descs, uint64_t n_steps, uint64_t first,
+                     cgl_stream_t stream);
 
 /* Out-of-place env step: as cgl_env_step / cgl_env_step_chained (token_dev == NULL: plain stream order;
  * otherwise the chained form), but the stability plane is READ from stable_in_dev and the new plane is
@@ -273,6 +317,37 @@ int cgl_env_step_host_async(uint32_t *world_in_dev, uint32_t *world_out_dev, int
                             int32_t *reward_dev_scratch, int32_t *reward_host, int8_t *obs_host,
                             cgl_stream_t stream);
 int cgl_stream_wait(cgl_stream_t stream);
+
+/* ---- host-driven rollout: the training loop's env side with the host out of the GPU's way -----------
+ * CGL/main.py:64-72 per step: the host hands every env an action (toggle_state, CGL/CGL.py:322-328), steps it
+ * (:247-252) and reads its reward (:255-256).  A rollout object owns n_groups GROUPS of envs_per_group environments
+ * (resident device planes supplied by the caller) that are stepped alternately, each on its own stream: while one
+ * group's step runs the host serves the other -- its rewards are read, `policy` fills its next actions, its next
+ * step is enqueued.  The data dependence (an env's next action may depend on its last reward) is kept per group:
+ * `policy` is called for a group only after that group's previous step has completed.
+ *   per group step   ONE cudaGraphLaunch of [H2D copy of the group's pinned int32 action buffer -> fused env step
+ *                    (-> D2H copy of the int8 observation plane if obs_host was given)]; the kernel writes the rewards
+ *                    straight into the group's pinned, host-mapped reward buffer; completion is an event the host polls.
+ *   n_replicas       every group rotates over n_replicas resident env batches (global step s uses replica s %
+ *                    n_replicas): lets a benchmark keep the working set above the L2 size.  1 = a plain rollout.
+ *   planes           world_a_dev / world_b_dev / stable_dev: [n_groups * n_replicas] device pointers, index
+ *                    group * n_replicas + replica; world_a holds the current world at creation.
+ *   obs_host         NULL, or [n_groups] pinned int8 buffers of envs_per_group * side^2 bytes.
+ * cgl_rollout_buffers: the group's pinned action (host writes) and reward (host reads) buffers, int32[envs_per_group];
+ *                    actions start as side*side ("do nothing").
+ * cgl_rollout_run:   `steps` steps of every group.  policy(user, group, step, reward_host, actions_host) may be NULL
+ *                    (the action buffers are then used as they are).  Returns when every group has finished.
+ * cgl_rollout_parity: 0 if (group, replica)'s current world is in its world_a plane, 1 if in world_b. */
+typedef struct cgl_rollout cgl_rollout_t;
+typedef void (*cgl_policy_fn)(void *user, uint32_t group, uint64_t step, const int32_t *reward_host,
+                              int32_t *actions_host);
+int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32_t n_replicas, uint32_t *const *world_a_dev,
+                       uint32_t *const *world_b_dev, int8_t *const *stable_dev, uint64_t envs_per_group,
+                       uint32_t side, int spawn, int stable_max, int8_t *const *obs_host);
+int cgl_rollout_buffers(cgl_rollout_t *r, uint32_t group, int32_t **actions_host, int32_t **reward_host);
+int cgl_rollout_run(cgl_rollout_t *r, uint64_t steps, cgl_policy_fn policy, void *user);
+int cgl_rollout_parity(const cgl_rollout_t *r, uint32_t group, uint32_t replica);
+int cgl_rollout_destroy(cgl_rollout_t *r);
 
 /* ---- CUDA IPC helpers for the row-band halo exchange over NVLink (multi-GPU life mode) ----
  * One process per GPU; each rank exports its ghost-row buffer and maps its neighbours'. */
