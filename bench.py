@@ -441,17 +441,16 @@ def measure_e2e(c, args, sims):
     torch = c.torch
     from cgl_b200.rollout import HostRollout
     B, R, size = ENVS_PER_GPU, REPLICAS, SIDE * SIDE
-    ke = max(10, min(args.steps, 200))
+    ke = 200                                                # (its own step count: a region of 200 full steps)
     reps = min(args.repeats, 5)
 
-    def make(obs):
+    def make(obs, zero_copy=False):
         return HostRollout(B, SIDE, n_groups=2, n_replicas=R, seed=c.rank * 10 ** 5 + 77, spawnStabilityFactor=SPAWN,
-                           stableStabilityFactor=STABLE, device=c.dev, rng="device", obs_to_host=obs)
+                           stableStabilityFactor=STABLE, device=c.dev, rng="device", obs_to_host=obs,
+                           zero_copy_actions=zero_copy)
 
-    idx = np.arange(0, B // 2, 64)
-
-    def policy(group, step, rewards, actions):              # reads rewards of the group's last step, writes actions
-        actions[idx] = (rewards[idx] + step) % (size + 1)
+    def policy(group, step, rewards, actions):              # reads a reward of the group's last step, writes an action
+        actions[step & 1023] = (int(rewards[step & 1023]) + step) % (size + 1)
 
     def wall(fn):
         c.barrier(); torch.cuda.synchronize()
@@ -469,6 +468,14 @@ def measure_e2e(c, args, sims):
     dts = [wall(lambda: ro.run(ke, policy)) for _ in range(reps)]
     dt_ro = statistics.median(dts)
     dts_np = [wall(lambda: ro.run(ke, None)) for _ in range(min(reps, 3))]
+    ro.close()
+    del ro
+    # variant: no copy node, the kernel reads the actions from the pinned buffer over PCIe
+    ro = make(False, zero_copy=True)
+    for g in range(2):
+        ro.actions[g][:] = np.random.RandomState(g).randint(size + 1, size=B // 2)
+    ro.run(4, policy)
+    dt_zc = statistics.median([wall(lambda: ro.run(ke, policy)) for _ in range(min(reps, 3))])
     ro.close()
     del ro
     # synchronous single call per step (the round-1 e2e): copy, launch, synchronise, repeat
@@ -500,6 +507,9 @@ def measure_e2e(c, args, sims):
                    "group); the observation stays device-resident for a GPU Q-network",
             "regions_us_per_step": [d / ke * 1e6 for d in dts],
             "without_policy_callback": {"value": cells * ke / statistics.median(dts_np) / 1e9, "unit": "Gcell-updates/s"},
+            "zero_copy_actions": {"value": cells * ke / dt_zc / 1e9, "unit": "Gcell-updates/s",
+                                  "what": "same rollout, no H2D copy node: the kernel loads each env's action from the "
+                                          "pinned host buffer over PCIe (4 B per env per step in the same direction)"},
             "synchronous_single_call": {"value": cells * ke / dt_sync / 1e9, "unit": "Gcell-updates/s",
                                         "us_per_step": dt_sync / ke * 1e6,
                                         "api": "BatchedSim.step_host -> cgl_env_step_host (copy, step, sync per step)"},

@@ -307,23 +307,33 @@ class sim:
         b = self._b
         if not self._fast:
             return self._step_now_batched(a)
-        key = b._wa.data_ptr()
-        args = self._fast_args.get(key)
+        args = self._fast_args.get("args")
         if args is None:
             import ctypes
+            from cgl_b200 import native
             from cgl_b200.batched import DEAD_RULES
-            V = ctypes.c_void_p
-            args = (V(b._wa.data_ptr()), V(b._wb.data_ptr()), V(b.stable.data_ptr()), self.side,
-                    b.spawn, b.stable_max, DEAD_RULES[b.dead_rule], b.empty, b.empty_min, int(b.masked_toggle),
-                    V(self._m_stable_t.data_ptr()), V(self._res_t.data_ptr()), b._lib.cgl_sim_step)
-            self._fast_args[key] = args
+            st = native.SimStepArgs()
+            st.world_a, st.world_b, st.stable = b._wa.data_ptr(), b._wb.data_ptr(), b.stable.data_ptr()
+            st.side, st.spawn, st.stable_max = self.side, b.spawn, b.stable_max
+            st.dead_rule, st.empty, st.empty_min = DEAD_RULES[b.dead_rule], b.empty, b.empty_min
+            st.masked_toggle = int(b.masked_toggle)
+            st.obs_mirror, st.result = self._m_stable_t.data_ptr(), self._res_t.data_ptr()
+            flip = ctypes.c_uint32(0)                        # even: the world is in the plane that is `world_a` here
+            st.flip_planes = ctypes.pointer(flip)
+            raw = getattr(self._torch._C, "_cuda_getCurrentRawStream", None)
+            args = (st, ctypes.byref(st), flip, b._lib.cgl_sim_step_ex, raw, self._dev.index, b._wa.data_ptr())
+            self._fast_args["args"] = args
+        # the planes this struct was built from may have been swapped by other calls (run, batched step, ...)
+        want_odd = b._wa.data_ptr() != args[6]
+        if bool(args[2].value & 1) != want_odd:
+            args[2].value = int(want_odd)
         self._wait()                                        # one step in flight at a time (the result block is shared)
         self._seq = seq = (self._seq + 1) & 0x3fffffff
         torch = self._torch
         if torch.cuda.current_device() != self._dev.index:
             torch.cuda.set_device(self._dev)
-        rc = args[12](args[0], args[1], args[2], args[3], a, args[4], args[5], args[6], args[7], args[8], args[9],
-                      args[10], args[11], seq, b._stream())
+        stream = args[4](args[5]) if args[4] is not None else torch.cuda.current_stream(self._dev).cuda_stream
+        rc = args[3](args[1], a, seq, stream)
         if rc:
             from cgl_b200 import native
             native.check(rc, "cgl_sim_step")

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgl_b200.so")
-SOURCES = ["cgl_api.cu", "cgl_env.cu", "cgl_env_tma.cu", "cgl_env_run.cu", "cgl_sim1.cu", "cgl_rollout.cu", "cgl_life.cu", "cgl_life_tb.cu"]
+SOURCES = ["cgl_api.cu", "cgl_env.cu", "cgl_env_tma.cu", "cgl_env_run.cu", "cgl_sim1.cu", "cgl_rollout.cu", "cgl_life.cu", "cgl_life_tb.cu", "cgl_life_persist.cu"]
 HEADERS = ["cgl_bits.cuh", "cgl_internal.cuh", os.path.join("..", "..", "include", "cgl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
@@ -49,5 +49,38 @@ def build(force=False, verbose=False):
     return LIB
 
 
+EXT_SRC = os.path.join(HERE, "csrc_ext", "cgl_torch_ext.cpp")
+EXT_LIB = os.path.join(HERE, "cgl_b200", "_cgl_ext.so")
+
+
+def build_ext(force=False):
+    """The thin PyTorch C++ extension (csrc_ext/cgl_torch_ext.cpp -> cgl_b200/_cgl_ext.so): g++ against torch's
+    headers, linked to libcgl_b200.so through an $ORIGIN rpath.  In-tree, so it travels with the gpurun snapshot."""
+    import sysconfig
+    build()
+    deps = [EXT_SRC, os.path.join(HERE, "..", "include", "cgl_b200.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(EXT_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(EXT_LIB) for d in deps):
+        return EXT_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    libdir = ce.library_paths()[0]
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_cgl_ext", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-Wno-deprecated-declarations"]
+    cmd += [f"-I{i}" for i in inc] + [EXT_SRC, "-o", EXT_LIB, f"-L{libdir}", f"-L{HERE}", "-lcgl_b200", "-ltorch_python",
+                                     "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda",
+                                     "-Wl,-rpath,$ORIGIN/..", f"-Wl,-rpath,{libdir}"]
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building cgl_b200/_cgl_ext.so")
+    return EXT_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--ext" in sys.argv:
+        print(build_ext(force="--force" in sys.argv))

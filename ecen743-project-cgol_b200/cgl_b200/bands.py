@@ -12,6 +12,14 @@ in from the buffer edges advances one row per generation and never reaches an ow
 Horizontal wrap is local.  Message = k * C/8 bytes per neighbour per k generations.
 
 Exchange back ends
+  "persist" ONE cooperative launch per run() call (`cgl_life_band_run`): a warp keeps its strip of
+          rows for all sub-steps of kernel_k generations and waits only for its neighbour strips; every k generations
+          the strips that own a rank's first / last k owned rows store them into the ring neighbours' landing zones
+          over NVLink (CUDA-IPC mapped peer memory, two slots) and bump an arrival counter, and the strips that read
+          ghost rows wait for the counter and copy what they need out of their own landing zone.  No exchange
+          launch, no launch boundary between sub-steps, interior strips never wait for another GPU.  Correct and
+          tested, but measured slower than "p2p" (the persistent kernel's row loop runs at 0.88 us per row step
+          against 0.60: DESIGN.md section 4.6), so it is opt-in.
   "fused" the halo exchange lives INSIDE the k-generation kernel
           (`cgl_life_band_block`): the strips that produce a rank's first/last k owned rows store
           them straight into the neighbours' next input buffers over NVLink (CUDA-IPC mapped peer
@@ -71,9 +79,14 @@ class RowBandLife:
             raise ValueError("band must have at least k rows")
         self.device = torch.device(device)
         self.group = group
-        self.exchange = exchange or ("single" if world_size == 1 else ("p2p" if self.device.type == "cuda" else "dist"))
         self.lib = lib if lib is not None else native.load()
-        g = self.k if self.G > 1 else 0
+        if exchange is None:
+            exchange = "single" if world_size == 1 else ("p2p" if self.device.type == "cuda" else "dist")
+        self.exchange = exchange
+        # a ring of ONE with exchange="persist" keeps its ghost rows and exchanges with itself (its upper and lower
+        # neighbour are the rank itself: the torus wrap) -- the in-kernel exchange on a single GPU (tests)
+        self._self_ring = self.G == 1 and self.exchange == "persist"
+        g = self.k if (self.G > 1 or self._self_ring) else 0
         self.ghost = g
         self.buf_rows = self.band_rows + 2 * g
         n = self.buf_rows * self.W
@@ -88,7 +101,7 @@ class RowBandLife:
         else:
             self._a = torch.zeros(n, dtype=torch.int32, device=self.device)
             self._b = torch.zeros(n, dtype=torch.int32, device=self.device)
-        if self.exchange == "p2p" and self.G > 1:
+        if self.exchange in ("p2p", "persist") and (self.G > 1 or self._self_ring):
             self._setup_p2p()
 
     # ---------------------------------------------------------------- state access
@@ -168,6 +181,9 @@ class RowBandLife:
             native.check(lib.cgl_dev_alloc(total, ctypes.byref(base)), "cgl_dev_alloc")
             handle = (ctypes.c_uint8 * 64)()
             native.check(lib.cgl_ipc_get_handle(base, handle), "cgl_ipc_get_handle")
+        if self.G == 1:                                     # ring of one: my neighbours are me
+            self._ipc = dict(base=base.value, strip=strip, up=base.value, down=base.value, flags_off=4 * strip, local=True)
+            return
         handles = [None] * self.G
         dist.all_gather_object(handles, bytes(handle), group=self.group)
         up, down = (self.rank - 1) % self.G, (self.rank + 1) % self.G
@@ -197,14 +213,29 @@ class RowBandLife:
                     self.lib.cgl_dev_free(ctypes.c_void_p(p))
             self._fused = None
         if self._ipc:
-            import torch.distributed as dist
             torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)
             with torch.cuda.device(self.device):
-                for p in {self._ipc["up"], self._ipc["down"]}:
-                    self.lib.cgl_ipc_close_handle(ctypes.c_void_p(p))
+                if not self._ipc.get("local"):
+                    import torch.distributed as dist
+                    dist.barrier(group=self.group)
+                    for p in {self._ipc["up"], self._ipc["down"]}:
+                        self.lib.cgl_ipc_close_handle(ctypes.c_void_p(p))
                 self.lib.cgl_dev_free(ctypes.c_void_p(self._ipc["base"]))
             self._ipc = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            if self._ipc and self._ipc.get("local"):        # (peer mappings need the collective close())
+                self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     # ---------------------------------------------------------------- halo exchange
     def _exchange(self):
@@ -252,14 +283,14 @@ class RowBandLife:
     def run(self, gens: int) -> None:
         """Advance `gens` generations (blocks of k generations between exchanges)."""
         lib, st = self.lib, self._stream()
-        if self.device.type == "cuda" and self.exchange != "fused" and not getattr(self, "_tuned", False):
+        if self.device.type == "cuda" and self.exchange not in ("fused", "persist") and not getattr(self, "_tuned", False):
             # measure the strip length of the k-blocked kernel for this band shape once (clobbers _b only)
             with torch.cuda.device(self.device):
                 native.check(lib.cgl_life_tune(native.dptr(self._a), native.dptr(self._b),
-                                               self.band_rows if self.G == 1 else self.buf_rows, self.cols,
-                                               1 if self.G == 1 else 0, self.kernel_k, st), "cgl_life_tune")
+                                               self.buf_rows, self.cols, 1 if self.ghost == 0 else 0, self.kernel_k,
+                                               st), "cgl_life_tune")
             self._tuned = True
-        if self.G == 1:                      # plain torus: one call, k generations per launch
+        if self.G == 1 and not self._self_ring:   # plain torus: one call, k generations per launch
             with torch.cuda.device(self.device) if self.device.type == "cuda" else _null():
                 if not _life_block(lib, self._a, self._b, self.band_rows, self.cols, 1, gens, self.kernel_k, st):
                     self._a, self._b = self._b, self._a
@@ -268,6 +299,8 @@ class RowBandLife:
             return
         if self.exchange == "fused":
             return self._run_fused(gens)
+        if self.exchange == "persist":
+            return self._run_persist(gens)
         done = 0
         while done < gens:
             kb = min(self.k, gens - done)
@@ -278,6 +311,47 @@ class RowBandLife:
             self.launches += -(-kb // self.kernel_k)
             done += kb
             self.generation += kb
+
+    def _run_persist(self, gens: int) -> None:
+        lib, ipc, st, kk = self.lib, self._ipc, self._stream(), self.kernel_k
+
+        def barrier():
+            if self.G > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)
+        if gens % kk:
+            raise ValueError(f"exchange='persist' runs whole sub-steps: gens must be a multiple of kernel_k = {kk}")
+        V = ctypes.c_void_p
+        if not self._ghosts_valid:
+            # fresh grid: zero the arrival counters on every rank, then the first call pushes the edge rows itself
+            torch.cuda.synchronize(self.device)
+            barrier()
+            with torch.cuda.device(self.device):
+                native.check(lib.cgl_dev_memset(V(ipc["base"] + ipc["flags_off"]), 0, 64, st), "cgl_dev_memset")
+            torch.cuda.synchronize(self.device)
+            barrier()
+            self.block = 0
+        strip, base, fo = ipc["strip"], ipc["base"], ipc["flags_off"]
+        up, down = ipc["up"], ipc["down"]
+        arr = V * 2
+        # my first owned rows -> the upper neighbour's "from below" zone; my last owned rows -> the lower one's "from above"
+        peer_up = arr(up + strip, up + 3 * strip)
+        peer_dn = arr(down, down + 2 * strip)
+        mine_up = arr(base, base + 2 * strip)
+        mine_dn = arr(base + strip, base + 3 * strip)
+        n_sub = gens // kk
+        with torch.cuda.device(self.device):
+            native.check(lib.cgl_life_band_run(
+                native.dptr(self._a), native.dptr(self._b), self.buf_rows, self.cols, self.ghost, kk, n_sub, self.block,
+                int(not self._ghosts_valid), peer_up, peer_dn, V(up + fo + 4), V(down + fo), mine_up, mine_dn,
+                V(base + fo), V(base + fo + 4), st), "cgl_life_band_run")
+        self._ghosts_valid = True
+        per_block = self.k // kk
+        self.block += -(-n_sub // per_block)
+        if n_sub & 1:
+            self._a, self._b = self._b, self._a
+        self.launches += 1
+        self.generation += gens
 
     _BLOCK_SIZES = (16, 12, 8, 6, 4, 3, 2, 1)       # generations one fused launch can do
 
@@ -325,7 +399,10 @@ class RowBandLife:
         if self.G > 1:
             import torch.distributed as dist
             dist.all_reduce(total, group=self.group)
-        return int(total.item())
+        n = int(total.item())
+        if self.device.type == "cuda":
+            native.check_alarm()                            # a device-side wait that gave up (see cgl_alarm_words)
+        return n
 
     def checksum(self) -> int:
         """Order-independent 64-bit hash of the whole grid (sum over words of word * f(global index)),
@@ -338,7 +415,10 @@ class RowBandLife:
         if self.G > 1:
             import torch.distributed as dist
             dist.all_reduce(total, group=self.group)
-        return int(total.item())
+        n = int(total.item())
+        if self.device.type == "cuda":
+            native.check_alarm()
+        return n
 
 
 class LocalBands:

@@ -363,21 +363,13 @@ class BatchedSim:
 
     def reward(self) -> torch.Tensor:
         """int32 [B] = sum of each env's stability vector (CGL/CGL.py:255-256)."""
-        out = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_reward(native.dptr(self.stable), self.n_envs, self.size,
-                                              native.dptr(out), self._stream()), "cgl_reward")
         self.launches += 1
-        return out
+        return native.ext().reward(self.stable, self.size)
 
     def alive(self) -> torch.Tensor:
         """int64 [B] live-cell counts (CGL/CGL.py:259-260)."""
-        out = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_alive(native.dptr(self._wa), self.n_envs, self.side * self.W,
-                                             native.dptr(out), self._stream()), "cgl_alive")
         self.launches += 1
-        return out.to(torch.int64) & 0xFFFFFFFF
+        return native.ext().alive(self._wa, self.side * self.W).to(torch.int64) & 0xFFFFFFFF
 
     def last_alive(self) -> torch.Tensor:
         """Live-cell counts written by the last step(want_alive=True)."""
@@ -385,12 +377,8 @@ class BatchedSim:
 
     def get_state(self) -> torch.Tensor:
         """uint8 [B, size] cells in the reference's array format (unpacked copy)."""
-        out = torch.empty((self.n_envs, self.size), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            native.check(self._lib.cgl_unpack(native.dptr(self._wa), native.dptr(out), self.n_envs,
-                                              self.side, self.side, self._stream()), "cgl_unpack")
         self.launches += 1
-        return out
+        return native.ext().unpack(self._wa, self.side, self.side)
 
     def get_stable(self) -> torch.Tensor:
         """int8 [B, size]: the live observation tensor (shallow, like get_stable(shallow=True))."""
@@ -559,7 +547,7 @@ class StepSequence:
                 native.check_alarm()
             descs, n, modes = self._descs()
             for s, mode in zip(sims, modes):
-                if mode == native.CHAIN_IDS or s._tok is None:
+                if mode and (mode == native.CHAIN_IDS or s._tok is None):
                     s._sync_tokens(mode, s._wa.data_ptr())
             rc = fn(descs, n, n_steps, 0, stream)
             if rc:

@@ -69,6 +69,9 @@ SIGNATURES = {
     "cgl_halo_wait": (_i, [_vp, _u32, _vp]),
     "cgl_halo_wait_copy": (_i, [_vp, _u32, _vp, _vp, _u64, _vp]),
     "cgl_life_band_block": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "cgl_life_band_run": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                               _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _vp]),
+    "cgl_life_band_run_supported": (_i, [_u32, _u32, _u32]),
     "cgl_dev_alloc": (_i, [_u64, ctypes.POINTER(_vp)]),
     "cgl_dev_free": (_i, [_vp]),
     "cgl_dev_memset": (_i, [_vp, _i, _u64, _vp]),
@@ -87,9 +90,19 @@ CHAIN_NONE, CHAIN_IDS, CHAIN_SEQ = 0, 1, 2
 SIGNATURES["cgl_env_step_ex"] = (_i, [ctypes.POINTER(EnvStepArgs), _vp])
 SIGNATURES["cgl_env_step_seq"] = (_i, [ctypes.POINTER(EnvStepArgs), _u32, _u64, _u64, _vp])
 
+class SimStepArgs(ctypes.Structure):
+    """cgl_sim_step_args_t (include/cgl_b200.h)."""
+    _fields_ = [("world_a", _vp), ("world_b", _vp), ("stable", _vp), ("side", _u32), ("spawn", ctypes.c_int32),
+                ("stable_max", ctypes.c_int32), ("dead_rule", ctypes.c_int32), ("empty", ctypes.c_int32),
+                ("empty_min", ctypes.c_int32), ("masked_toggle", ctypes.c_int32), ("obs_mirror", _vp), ("result", _vp),
+                ("flip_planes", ctypes.POINTER(_u32))]
+
+
+SIGNATURES["cgl_sim_step_ex"] = (_i, [ctypes.POINTER(SimStepArgs), ctypes.c_int32, _u32, _vp])
+
 POLICY_FN = ctypes.CFUNCTYPE(None, _vp, _u32, _u64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32))
 SIGNATURES["cgl_rollout_create"] = (_i, [ctypes.POINTER(_vp), _u32, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
-                                         ctypes.POINTER(_vp), _u64, _u32, _i, _i, ctypes.POINTER(_vp)])
+                                         ctypes.POINTER(_vp), _u64, _u32, _i, _i, ctypes.POINTER(_vp), _u32])
 SIGNATURES["cgl_rollout_buffers"] = (_i, [_vp, _u32, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
                                           ctypes.POINTER(ctypes.POINTER(ctypes.c_int32))])
 SIGNATURES["cgl_rollout_run"] = (_i, [_vp, _u64, _vp, _vp])
@@ -127,6 +140,26 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         raise CglNativeError("libcgl_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+_ext = None
+
+
+def ext():
+    """The thin PyTorch C++ extension (csrc_ext/cgl_torch_ext.cpp -> cgl_b200/_cgl_ext.so): torch-typed entry points
+    over the same C ABI.  Built by build.py (build_ext); a missing extension raises -- nothing falls back."""
+    global _ext
+    if _ext is None:
+        load()                                  # libcgl_b200.so first: the extension links against it
+        try:
+            from . import _cgl_ext as mod
+        except ImportError as exc:
+            raise CglNativeError(f"cgl_b200/_cgl_ext.so is missing or does not load ({exc}): build it with "
+                                 f"`python {_PKG_DIR}/build.py --ext`") from exc
+        if mod.abi_version() != 1:
+            raise CglNativeError("_cgl_ext.so was built against another ABI version")
+        _ext = mod
+    return _ext
 
 
 def check(rc: int, what: str = "") -> None:

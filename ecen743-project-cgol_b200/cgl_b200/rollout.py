@@ -28,7 +28,7 @@ from .batched import BatchedSim
 class HostRollout:
     def __init__(self, n_envs: int, side: int, n_groups: int = 2, n_replicas: int = 1, seed: int = 0,
                  spawnStabilityFactor: int = -1, stableStabilityFactor: int = 1, device="cuda", rng: str = "reference",
-                 first_env: int = 0, obs_to_host: bool = False):
+                 first_env: int = 0, obs_to_host: bool = False, zero_copy_actions: bool = False):
         if n_envs % n_groups:
             raise ValueError("n_envs must be divisible by n_groups")
         self._lib = native.load()
@@ -60,7 +60,7 @@ class HostRollout:
             torch.cuda.synchronize()
             native.check(self._lib.cgl_rollout_create(ctypes.byref(self._h), n_groups, n_replicas, wa, wb, st,
                                                       self.per_group, side, spawnStabilityFactor, stableStabilityFactor,
-                                                      obs_ptrs), "cgl_rollout_create")
+                                                      obs_ptrs, int(bool(zero_copy_actions))), "cgl_rollout_create")
         self.actions, self.rewards = [], []
         for g in range(n_groups):
             a = ctypes.POINTER(ctypes.c_int32)()
@@ -69,6 +69,7 @@ class HostRollout:
             self.actions.append(np.ctypeslib.as_array(a, shape=(self.per_group,)))
             self.rewards.append(np.ctypeslib.as_array(r, shape=(self.per_group,)))
         self.steps = 0
+        self.zero_copy_actions = bool(zero_copy_actions)
         self.h2d_bytes_per_step = 4 * n_envs
         self.d2h_bytes_per_step = 4 * n_envs + (n_envs * self.size if obs_to_host else 0)
 

@@ -113,6 +113,7 @@ static int apply_hooks()
     int rc;
     if ((rc = set_hooks_env(g_alarm_dev, g_wait_ns_host))) return rc;
     if ((rc = set_hooks_life_tb(g_alarm_dev, g_wait_ns_host))) return rc;
+    if ((rc = set_hooks_life_persist(g_alarm_dev, g_wait_ns_host))) return rc;
     return set_hooks_api(g_alarm_dev, g_wait_ns_host);
 }
 

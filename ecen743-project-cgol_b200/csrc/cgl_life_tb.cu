@@ -238,22 +238,174 @@ life_tb_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Direct pipeline (no skew) with a triangular start-up.  Level g+1 consumes level g's row in the SAME row step, so
+// a strip of L rows costs L + 2K steps instead of L + 3K - 1, and during the first 2K steps level g is skipped
+// until step 2g (nothing it could produce before is needed): the start-up costs K(K+1) level-steps = (K+1)/2 full
+// steps' worth of work on top of the K dead rows -- 9 instead of 23 step equivalents for K = 8.  That matters where
+// strips are short: the 8192-row bands of the 8-GPU C4 run (~200-row strips) spend 10 % of every launch in the
+// fill of the skewed pipeline.  Parallelism inside a warp now comes from the wavefront over the unrolled row steps
+// (step u+1 of level g and step u of level g+1 are independent) instead of from K independent levels.
+// Same strip geometry, chaining and ghost-zone contract as life_tb_kernel (non-HALO).
+template <int K, bool PRO>
+__device__ __forceinline__ void tb2_block(const uint32_t (&raw)[TB_UNROLL], Win (&win)[K], int s0, uint32_t *op, uint32_t r0W,
+                                          uint32_t W, bool store_ok, uint32_t out_rows)
+{
+#pragma unroll
+    for (int u = 0; u < TB_UNROLL; ++u) {
+        uint32_t x = raw[u];
+#pragma unroll
+        for (int g = 0; g < K; ++g) {
+            if (PRO && s0 + u < 2 * g) {             // warp-uniform: this level has nothing to do yet
+                x = 0;
+                continue;
+            }
+            const uint32_t left = __shfl_up_sync(0xffffffffu, x, 1);
+            const uint32_t right = __shfl_down_sync(0xffffffffu, x, 1);
+            const HSum d = hsum(west_plane(left, x), x, east_plane(x, right));
+            const HSum up = {win[g].us0, win[g].us1, 0, 0};
+            const HSum mid = {0, 0, win[g].mt0, win[g].mt1};
+            const uint32_t y = life_rule(up, mid, d, win[g].mc);
+            win[g].us0 = win[g].ms0; win[g].us1 = win[g].ms1;
+            win[g].ms0 = d.s0; win[g].ms1 = d.s1; win[g].mt0 = d.t0; win[g].mt1 = d.t1; win[g].mc = x;
+            x = y;
+        }
+        // row r0 + so of generation K has just left level K
+        const uint32_t so = (uint32_t)(s0 + u - 2 * K);
+        st_if_lt(op + r0W + so * W, x, store_ok, so, out_rows);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TB_THREADS)
+life_tb2_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t rows, uint32_t W, uint32_t rpt,
+                int wrap_rows, uint32_t n_cgroups, uint32_t n_rblocks, const ChainCtx chain)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t cg = warp % n_cgroups;
+    uint32_t rb = warp / n_cgroups;
+    const bool warp_ok = rb < n_rblocks;
+    rb = warp_ok ? rb : n_rblocks - 1;
+    bool wait_ok = true;
+
+    if (chain.tokens != nullptr) {                             // kernel-uniform branch (see life_tb_kernel)
+        cudaTriggerProgrammaticLaunchCompletion();
+        const int dj = (int)(lane % 3) - 1, di = (int)(lane / 3) - 1;
+        const uint32_t ncg = (cg + n_cgroups + (uint32_t)dj) % n_cgroups;
+        int nrb = (int)rb + di;
+        bool need = lane < 9;
+        if (nrb < 0 || nrb >= (int)n_rblocks) {
+            if (wrap_rows) nrb = nrb < 0 ? nrb + (int)n_rblocks : nrb - (int)n_rblocks;
+            else need = false;
+        }
+        const uint32_t *tp = chain.tokens + (need ? (uint32_t)nrb * n_cgroups + ncg : 0u);
+        uint32_t v, spins = 0;
+        unsigned long long t0 = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tp) : "memory");
+            if (__all_sync(0xffffffffu, !need || (int32_t)(v - chain.want) >= 0)) break;
+            if (spins == 0) t0 = globaltimer_ns();
+            if ((++spins & 255u) == 0 && __any_sync(0xffffffffu, wait_expired(t0, ALARM_LIFE_TOKEN))) {
+                wait_ok = false;
+                if (lane == 0) raise_alarm(ALARM_LIFE_TOKEN);
+                break;
+            }
+        }
+    }
+
+    const int wi = (int)(cg * TB_COLS + lane) - 1;
+    const uint32_t wcol = wi < 0 ? (uint32_t)(wi + (int)W) : ((uint32_t)wi >= W ? (uint32_t)wi - W : (uint32_t)wi);
+    const bool store_ok = warp_ok && wait_ok && lane >= 1 && lane <= TB_COLS && (uint32_t)wi < W;
+    const int r0 = (int)(rb * rpt);
+    const int r1 = (r0 + (int)rpt < (int)rows) ? r0 + (int)rpt : (int)rows;
+    const int irows = (int)rows;
+    const int rstart = r0 - K;
+    const int n_steps = (int)rpt + 2 * K;                       // same trip count for every warp
+    const int s_lo = wrap_rows ? 0 : (rstart < 0 ? -rstart : 0);
+    const int last = (wrap_rows || r1 + K < irows) ? r1 + K : irows;
+    const uint32_t span = (uint32_t)(last - rstart - s_lo);
+    const uint32_t out_rows = (uint32_t)(r1 - r0);
+    int rw = rstart < 0 ? rstart + irows : rstart;
+    const uint32_t *ip = in + wcol;
+    uint32_t *op = out + (store_ok ? (uint32_t)wi : 0u);
+    const uint32_t r0W = (uint32_t)r0 * W;
+
+    Win win[K];
+#pragma unroll
+    for (int g = 0; g < K; ++g) win[g] = Win{0, 0, 0, 0, 0, 0, 0};
+
+    auto load = [&](uint32_t (&raw)[TB_UNROLL], int s0) {
+#pragma unroll
+        for (int u = 0; u < TB_UNROLL; ++u) {
+            const uint32_t ru = umin((uint32_t)rw + u, (uint32_t)rw + u - rows);
+            raw[u] = 0;
+            if ((uint32_t)(s0 + u - s_lo) < span) raw[u] = __ldg(ip + ru * W);
+        }
+        rw += TB_UNROLL;
+        rw = rw >= irows ? rw - irows : rw;
+    };
+    constexpr int PRO_STEPS = (2 * K + TB_UNROLL - 1) / TB_UNROLL * TB_UNROLL;      // start-up: levels come in one by one
+    int s0 = 0;
+    for (; s0 < PRO_STEPS && s0 < n_steps; s0 += TB_UNROLL) {
+        uint32_t raw[TB_UNROLL];
+        load(raw, s0);
+        tb2_block<K, true>(raw, win, s0, op, r0W, W, store_ok, out_rows);
+    }
+    for (; s0 < n_steps; s0 += TB_UNROLL) {
+        uint32_t raw[TB_UNROLL];
+        load(raw, s0);
+        tb2_block<K, false>(raw, win, s0, op, r0W, W, store_ok, out_rows);
+    }
+    if (chain.tokens != nullptr) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0 && warp_ok && wait_ok)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain.tokens + rb * n_cgroups + cg),
+                         "r"(chain.want + 1) : "memory");
+    }
+}
+
+// Which pipeline a K-generation launch uses: 1 = direct (life_tb2_kernel), 0 = skewed (life_tb_kernel).  Measured on
+// B200 (profiles/r02_sweeps.md), us per generation direct vs skewed -- one 8-GPU band of C4 (8320 x 65536): K = 2
+// 28.8 / 34.8, 4: 17.8 / 23.7, 6: 17.5 / 23.6, 8: 16.2 / 16.8, 12: 16.8 / 18.2, 16: 18.8 / 18.1; 32768^2: K = 2
+// 41.0 / 65.1, 4: 33.4 / 45.4, 8: 30.5 / 31.2, 16: 34.1 / 35.1.  The direct pipeline wins wherever the K levels fit
+// the register file with room to overlap row steps; at K = 16 (164 registers, 3 CTAs per SM) it is a tie and the
+// skewed one stays.  CGL_TB_MODE=0/1 forces one.
+static int tb_mode(int K)
+{
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("CGL_TB_MODE");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return forced;
+    return K <= 12 ? 1 : 0;
+}
+
 // Strip length for a (rows x cols) grid.  A strip costs rpt + 3K - 1 row steps (pipeline fill), and
 // the grid runs in ceil(CTAs / resident CTAs) waves of equally long CTAs; pick the candidate that
 // minimises waves x steps (measured on B200, profiles/r01_sweeps.md: both effects are real, and
 // fewer than ~3 waves balance badly, which the 0.97 factor for >= 3 waves encodes).
 static uint32_t tb_pick_rows(uint32_t rows, uint32_t n_cgroups, int K, uint64_t slot_ctas)
 {
-    static const uint32_t cand[] = {96, 128, 160, 192, 224, 256, 320, 384, 448, 512, 640, 768, 1024};
+    // candidates: a ladder of lengths plus the lengths that fill exactly one, two or three waves of resident CTAs
+    uint32_t cand[16] = {96, 128, 160, 192, 224, 256, 320, 384, 448, 512, 640, 768, 1024};
+    int n_cand = 13;
+    for (uint64_t w = 1; w <= 3; ++w) {
+        const uint64_t rb = (w * slot_ctas * (TB_THREADS / 32)) / n_cgroups;
+        if (rb >= 1) cand[n_cand++] = (uint32_t)((rows + rb - 1) / rb);
+    }
     uint32_t best = 256;
     double best_t = 1e30;
-    for (uint32_t rpt : cand) {
+    for (int ci = 0; ci < n_cand; ++ci) {
+        const uint32_t rpt = cand[ci];
         if (rpt < 8u * K) continue;
         const uint32_t eff = rpt < rows ? rpt : rows;
         const uint64_t warps = (uint64_t)n_cgroups * ((rows + eff - 1) / eff);
         const uint64_t ctas = (warps + TB_THREADS / 32 - 1) / (TB_THREADS / 32);
         const uint64_t waves = (ctas + slot_ctas - 1) / slot_ctas;
-        double t = (double)waves * (eff + 3 * K - 1);
+        double t = (double)waves * (eff + 2 * K + 2);
         if (waves >= 3) t *= 0.97;
         if (t < best_t) { best_t = t; best = eff; }
     }
@@ -292,7 +444,10 @@ static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t 
         const char *e = getenv("CGL_TB_ROWS");
         rpt_knob = e ? atoi(e) : 0;
         int n = 0;
-        CGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, life_tb_kernel<K, HALO>, TB_THREADS, 0));
+        if (!HALO && tb_mode(K) == 1)
+            CGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, life_tb2_kernel<K>, TB_THREADS, 0));
+        else
+            CGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, life_tb_kernel<K, HALO>, TB_THREADS, 0));
         occ = n > 0 ? n : 1;
     }
     const uint32_t W = cols / 32;
@@ -324,6 +479,12 @@ static int launch_tb(const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (chain.tokens != nullptr && chain.want > 0) ? 1 : 0;        // the first launch of a run waits normally
+    if constexpr (!HALO) {
+        if (tb_mode(K) == 1) {
+            CGL_CUDA(cudaLaunchKernelEx(&cfg, life_tb2_kernel<K>, in, out, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, chain));
+            return 0;
+        }
+    }
     CGL_CUDA(cudaLaunchKernelEx(&cfg, life_tb_kernel<K, HALO>, in, out, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks,
                                 halo, chain));
     return 0;
@@ -419,6 +580,19 @@ extern "C" int cgl_life_run(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, uin
     uint32_t chained = 0;                 // launches of the current chain so far
     while (left > 0) {
         int step = 1;
+        if (tiled && (k == 4 || k == 8 || k == 16) && left >= 2 * k && !g_fault_next_chain) {
+            // the bulk of the run in ONE cooperative launch: a warp keeps its strip for all sub-steps and
+            // synchronises with its neighbour strips only (cgl_life_persist.cu)
+            const uint32_t n_sub = left / k;
+            const int rc = life_persist_run(src, dst, rows, cols, wrap_rows, n_sub, (int)k, st);
+            if (rc == 0) {
+                if (n_sub & 1u) { uint32_t *t = src; src = dst; dst = t; }
+                left -= n_sub * k;
+                prev_step = 0;
+                continue;
+            }
+            if (rc != -100) return rc;
+        }
         if (tiled && k > 1) {
             for (int s : sizes)
                 if ((uint32_t)s <= k && (uint32_t)s <= left) { step = s; break; }
@@ -466,7 +640,20 @@ extern "C" int cgl_life_tune(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, ui
     cudaEvent_t e0, e1;
     CGL_CUDA(cudaEventCreate(&e0));
     CGL_CUDA(cudaEventCreate(&e1));
-    static const uint32_t cand[] = {96, 128, 160, 192, 224, 256, 320, 384, 512, 640, 768};
+    uint32_t cand[16] = {96, 128, 160, 192, 224, 256, 320, 384, 512, 640, 768};
+    int n_cand = 11;
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, life_tb2_kernel<8>, TB_THREADS, 0) != cudaSuccess || occ <= 0) {
+            cudaGetLastError();
+            occ = 5;
+        }
+        const uint32_t n_cg = (W + TB_COLS - 1) / TB_COLS;
+        for (uint64_t w = 1; w <= 3; ++w) {              // exactly w waves of resident CTAs
+            const uint64_t rb = (w * (uint64_t)sm_count() * occ * (TB_THREADS / 32)) / n_cg;
+            if (rb >= 1) cand[n_cand++] = (uint32_t)((rows + rb - 1) / rb);
+        }
+    }
     float best_ms = 1e30f;
     uint32_t best = 0;
     TunedRows &slot = g_tuned[g_n_tuned];
@@ -474,7 +661,8 @@ extern "C" int cgl_life_tune(uint32_t *buf_a, uint32_t *buf_b, uint32_t rows, ui
     ++g_n_tuned;                                   // visible to launch_tb through tuned_rows()
     uint32_t token_cap = 0;
     uint32_t *token_buf = chain_tokens(st, rows, cols, &token_cap);
-    for (uint32_t rpt : cand) {
+    for (int ci = 0; ci < n_cand; ++ci) {
+        const uint32_t rpt = cand[ci];
         if (rpt < 8u * kk || rpt > rows) continue;
         slot.rpt = rpt;
         // time 4 launches chained like cgl_life_run chains them (all a -> b: every launch writes the same

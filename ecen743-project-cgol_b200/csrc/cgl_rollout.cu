@@ -37,7 +37,7 @@ struct cgl_rollout {
     };
     struct Group {
         std::vector<Replica> rep;
-        int32_t *act_host, *act_dev, *rew_host, *rew_dev_alias, *rew_dev;
+        int32_t *act_host, *act_dev, *act_dev_alias, *rew_host, *rew_dev_alias, *rew_dev;
         int8_t *obs_host;
         cudaStream_t st;
         cudaEvent_t ev;
@@ -48,6 +48,7 @@ struct cgl_rollout {
     uint64_t n;                             // envs per group
     uint32_t side, n_replicas;
     int spawn, stable_max, device;
+    bool zero_copy;                         // the kernel reads the actions straight from pinned host memory
     uint64_t step;                          // global step counter (all groups stepped `step` times)
 };
 
@@ -89,7 +90,7 @@ extern "C" int cgl_rollout_destroy(cgl_rollout_t *r)
 extern "C" int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32_t n_replicas,
                                   uint32_t *const *world_a_dev, uint32_t *const *world_b_dev,
                                   int8_t *const *stable_dev, uint64_t envs_per_group, uint32_t side, int spawn,
-                                  int stable_max, int8_t *const *obs_host)
+                                  int stable_max, int8_t *const *obs_host, uint32_t flags)
 {
     CGL_REQUIRE(out && n_groups >= 1 && n_groups <= 16 && n_replicas >= 1 && n_replicas <= 64 && world_a_dev &&
                     world_b_dev && stable_dev && envs_per_group && side,
@@ -98,6 +99,7 @@ extern "C" int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32
     CGL_REQUIRE(r, CGL_E_NOMEM, "cgl_rollout_create: out of memory");
     r->n = envs_per_group; r->side = side; r->n_replicas = n_replicas; r->spawn = spawn; r->stable_max = stable_max;
     r->step = 0;
+    r->zero_copy = (flags & CGL_ROLLOUT_ZERO_COPY_ACTIONS) != 0;
     int rc = 0;
 #define RB_CUDA(expr)                                                                                     \
     do {                                                                                                  \
@@ -119,7 +121,8 @@ extern "C" int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32
         gr.obs_host = obs_host ? obs_host[gi] : nullptr;
         RB_CUDA(cudaStreamCreateWithFlags(&gr.st, cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming));
-        RB_CUDA(cudaHostAlloc(&gr.act_host, abytes, cudaHostAllocPortable));
+        RB_CUDA(cudaHostAlloc(&gr.act_host, abytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        RB_CUDA(cudaHostGetDevicePointer(&gr.act_dev_alias, gr.act_host, 0));
         RB_CUDA(cudaHostAlloc(&gr.rew_host, abytes, cudaHostAllocMapped | cudaHostAllocPortable));
         RB_CUDA(cudaHostGetDevicePointer(&gr.rew_dev_alias, gr.rew_host, 0));
         RB_CUDA(cudaMalloc(&gr.act_dev, abytes));
@@ -144,9 +147,11 @@ extern "C" int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32
             for (int p = 0; p < 2; ++p) {        // one graph per plane orientation: copy -> step (-> obs copy)
                 cudaGraph_t graph = nullptr;
                 RB_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
-                cudaError_t e1 = cudaMemcpyAsync(gr.act_dev, gr.act_host, abytes, cudaMemcpyHostToDevice, gr.st);
+                cudaError_t e1 = cudaSuccess;
+                if (!r->zero_copy) e1 = cudaMemcpyAsync(gr.act_dev, gr.act_host, abytes, cudaMemcpyHostToDevice, gr.st);
                 g_pdl_suppress = 1;              // (the step follows a copy node: nothing to overlap with)
-                rc = cgl_env_step(rp.plane[p], rp.plane[p ^ 1], rp.stable, envs_per_group, side, gr.act_dev, spawn,
+                rc = cgl_env_step(rp.plane[p], rp.plane[p ^ 1], rp.stable, envs_per_group, side,
+                                  r->zero_copy ? gr.act_dev_alias : gr.act_dev, spawn,
                                   stable_max, direct ? gr.rew_dev_alias : gr.rew_dev, nullptr, nullptr, gr.st);
                 g_pdl_suppress = 0;
                 cudaError_t e2 = cudaSuccess;

@@ -21,72 +21,91 @@
 
 namespace cgl {
 
-constexpr uint32_t SIM1_MAX_SIDE = 320;          // two byte planes: 2 * 320^2 = 204,800 B of shared memory
+constexpr uint32_t SIM1_MAX_SIDE = 448;          // one byte plane + the packed next world: 448^2 + 448 * 56 B of shared memory
 
+// Thread layout: a thread serves FOUR consecutive cells of one row (the last thread of a row fewer); TPR threads per
+// row, blockDim / TPR rows per pass.  One division per thread, none per cell.
 __global__ void __launch_bounds__(1024)
 sim1_step_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out, int8_t *stable,
                  uint32_t side, uint32_t W, uint32_t action, int8_t spawn, int8_t stable_max, int rule, int8_t empty,
-                 int8_t empty_min, int masked, int8_t *obs_mirror, int32_t *result, uint32_t seq)
+                 int8_t empty_min, int masked, int8_t *obs_mirror, int32_t *result, uint32_t seq, uint32_t tpr,
+                 uint32_t rows_per_pass)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    const uint32_t size = side * side;
-    uint8_t *a = smem_dyn, *b = a + size;
+    const uint32_t size = side * side, n_words = side * W;
+    uint8_t *a = smem_dyn;                                        // current world, one byte per cell
+    uint32_t *nw = reinterpret_cast<uint32_t *>(smem_dyn + ((size + 15u) & ~15u));     // next world, packed
     __shared__ int red[2];
+    const uint32_t ty = threadIdx.x / tpr, x0 = (threadIdx.x - ty * tpr) * 4;
+    const bool lane_ok = ty < rows_per_pass;
+    const uint32_t nx = side - x0 < 4 ? side - x0 : 4;            // cells of this thread (x0 < side by construction)
     if (threadIdx.x == 0) { red[0] = 0; red[1] = 0; }
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) nw[i] = 0;
     // world bits -> bytes, the toggle applied on the way (action == size: nothing to toggle)
-    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) {
-        const uint32_t y = i / side, x = i - y * side;
-        uint8_t v = (world_in[y * W + (x >> 5)] >> (x & 31)) & 1u;
-        if (i == action) v ^= 1u;
-        a[i] = v;
-    }
-    __syncthreads();
-
-    // four cells per thread and trip: one 32-bit access to the stability plane and to the mirror
-    int acc = 0;
-    for (uint32_t base = threadIdx.x * 4; base < size; base += blockDim.x * 4) {
-        const uint32_t n = size - base < 4 ? size - base : 4;
-        uint32_t sv = 0;
-        if (n == 4) sv = *reinterpret_cast<const uint32_t *>(stable + base);
-        else for (uint32_t k = 0; k < n; ++k) sv |= (uint32_t)(uint8_t)stable[base + k] << (8 * k);
-        uint32_t out = 0;
-        for (uint32_t k = 0; k < n; ++k) {
-            const uint32_t i = base + k;
-            const uint32_t y = i / side, x = i - y * side;
-            const uint32_t yu = (y == 0 ? side : y) - 1, yd = (y + 1 == side) ? 0 : y + 1;
-            const uint32_t xl = (x == 0 ? side : x) - 1, xr = (x + 1 == side) ? 0 : x + 1;
-            const uint32_t cnt = a[yu * side + xl] + a[yu * side + x] + a[yu * side + xr] + a[y * side + xl] +
-                                 a[y * side + xr] + a[yd * side + xl] + a[yd * side + x] + a[yd * side + xr];
-            const uint8_t p = a[i];
-            const uint8_t q = (cnt == 3u) || (cnt == 2u && p);
-            b[i] = q;
-            int8_t s = (int8_t)(sv >> (8 * k));
-            // toggle_state: SPAWN (base env: even when toggled to dead, N2; fork: 0 then)
-            if (i == action) s = (masked && !p) ? (int8_t)0 : spawn;
-            s = stable_update1_rule(rule, s, p != 0, q != 0, spawn, stable_max, empty, empty_min);
-            acc += s;
-            out |= (uint32_t)(uint8_t)s << (8 * k);
-        }
-        if (n == 4) {
-            *reinterpret_cast<uint32_t *>(stable + base) = out;
-            if (obs_mirror != nullptr) *reinterpret_cast<uint32_t *>(obs_mirror + base) = out;
-        } else {
-            for (uint32_t k = 0; k < n; ++k) {
-                stable[base + k] = (int8_t)(out >> (8 * k));
-                if (obs_mirror != nullptr) obs_mirror[base + k] = (int8_t)(out >> (8 * k));
+    if (lane_ok)
+        for (uint32_t y = ty; y < side; y += rows_per_pass) {
+            const uint32_t bits = world_in[y * W + (x0 >> 5)] >> (x0 & 31);        // x0 % 4 == 0: one word
+            for (uint32_t k = 0; k < nx; ++k) {
+                const uint32_t i = y * side + x0 + k;
+                a[i] = (uint8_t)(((bits >> k) & 1u) ^ (i == action ? 1u : 0u));
             }
         }
-    }
+    __syncthreads();
+
+    int acc = 0;
+    const bool vec = (side & 3u) == 0;                            // rows start 4-byte aligned: one 32-bit access
+    if (lane_ok)
+        for (uint32_t y = ty; y < side; y += rows_per_pass) {
+            const uint32_t yu = (y == 0 ? side : y) - 1, yd = (y + 1 == side) ? 0 : y + 1;
+            const uint8_t *ru = a + yu * side, *rc = a + y * side, *rd = a + yd * side;
+            const uint32_t base = y * side + x0;
+            uint32_t sv = 0;
+            if (vec) sv = *reinterpret_cast<const uint32_t *>(stable + base);
+            else for (uint32_t k = 0; k < nx; ++k) sv |= (uint32_t)(uint8_t)stable[base + k] << (8 * k);
+            // column sums of the three rows for x0-1 .. x0+nx (torus columns)
+            uint32_t col3[6], mid[6];
+#pragma unroll
+            for (uint32_t k = 0; k < 6; ++k) {
+                if (k >= nx + 2) break;
+                uint32_t x = x0 + k;                               // column x - 1
+                x = x == 0 ? side - 1 : (x - 1 >= side ? x - 1 - side : x - 1);
+                mid[k] = rc[x];
+                col3[k] = ru[x] + mid[k] + rd[x];
+            }
+            uint32_t out = 0, nbits = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                if (k >= nx) break;
+                const uint32_t p = mid[k + 1];
+                const uint32_t cnt = col3[k] + col3[k + 1] + col3[k + 2] - p;
+                const uint32_t q = (cnt == 3u) || (cnt == 2u && p);
+                nbits |= q << k;
+                int8_t s = (int8_t)(sv >> (8 * k));
+                // toggle_state: SPAWN (base env: even when toggled to dead, N2; fork: 0 then)
+                if (base + k == action) s = (masked && !p) ? (int8_t)0 : spawn;
+                s = stable_update1_rule(rule, s, p != 0, q != 0, spawn, stable_max, empty, empty_min);
+                acc += s;
+                out |= (uint32_t)(uint8_t)s << (8 * k);
+            }
+            if (nbits) atomicOr(&nw[y * W + (x0 >> 5)], nbits << (x0 & 31));
+            if (vec) {
+                *reinterpret_cast<uint32_t *>(stable + base) = out;
+                if (obs_mirror != nullptr) *reinterpret_cast<uint32_t *>(obs_mirror + base) = out;
+            } else {
+                for (uint32_t k = 0; k < nx; ++k) {
+                    stable[base + k] = (int8_t)(out >> (8 * k));
+                    if (obs_mirror != nullptr) obs_mirror[base + k] = (int8_t)(out >> (8 * k));
+                }
+            }
+        }
     if (obs_mirror != nullptr) __threadfence_system();       // my mirror stores are visible to the host ...
     __syncthreads();                                          // ... before anyone publishes the sequence number
 
     uint32_t pop = 0;
-    for (uint32_t wdx = threadIdx.x; wdx < side * W; wdx += blockDim.x) {
-        const uint32_t y = wdx / W, x0 = (wdx - y * W) * 32;
-        uint32_t word = 0;
-        for (uint32_t j = 0; j < 32 && x0 + j < side; ++j) word |= (uint32_t)b[y * side + x0 + j] << j;
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
+        const uint32_t word = nw[i];
         pop += __popc(word);
-        world_out[wdx] = word;
+        world_out[i] = word;
     }
     acc = __reduce_add_sync(0xffffffffu, acc);
     pop = __reduce_add_sync(0xffffffffu, pop);
@@ -126,13 +145,29 @@ extern "C" int cgl_sim_step(const uint32_t *world_in, uint32_t *world_out, int8_
     static PerDeviceOnce once;
     if (once.first())
         CGL_CUDA(cudaFuncSetAttribute(sim1_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      2 * SIM1_MAX_SIDE * SIM1_MAX_SIDE));
-    // a thread serves four cells per trip; one trip for side <= 64
-    unsigned threads = ((size + 3) / 4 + 31) / 32 * 32;
-    threads = threads > 1024 ? 1024 : threads;
-    sim1_step_kernel<<<1, threads, 2 * size, as_stream(stream)>>>(
-        world_in, world_out, stable, side, cgl_words_per_row(side), (uint32_t)action, (int8_t)spawn,
-        (int8_t)stable_max, dead_rule, (int8_t)empty, (int8_t)empty_min, masked_toggle, obs_mirror, result, seq);
+                                      SIM1_MAX_SIDE * SIM1_MAX_SIDE + 16 + 4 * SIM1_MAX_SIDE * ((SIM1_MAX_SIDE + 31) / 32)));
+    // four cells per thread, whole rows per pass; all rows in one pass where 1024 threads allow it (side <= 64)
+    const uint32_t W = cgl_words_per_row(side), tpr = (side + 3) / 4;
+    uint32_t rows_per_pass = 1024 / tpr;
+    if (rows_per_pass > side) rows_per_pass = side;
+    const unsigned threads = (tpr * rows_per_pass + 31) / 32 * 32;
+    const size_t smem = ((size + 15u) & ~15u) + 4 * (size_t)side * W;
+    sim1_step_kernel<<<1, threads, smem, as_stream(stream)>>>(
+        world_in, world_out, stable, side, W, (uint32_t)action, (int8_t)spawn, (int8_t)stable_max, dead_rule,
+        (int8_t)empty, (int8_t)empty_min, masked_toggle, obs_mirror, result, seq, tpr, rows_per_pass);
     CGL_LAUNCH_CHECK();
     return 0;
+}
+
+// Struct form for bindings: the per-env constants and pointers are filled once, a step passes one pointer plus the
+// two values that change (see include/cgl_b200.h).
+extern "C" int cgl_sim_step_ex(const cgl_sim_step_args_t *a, int32_t action, uint32_t seq, cgl_stream_t stream)
+{
+    CGL_REQUIRE(a, CGL_E_BADARG, "cgl_sim_step_ex: null");
+    const bool flip = (a->flip_planes != nullptr) && (*a->flip_planes & 1u);
+    const int rc = cgl_sim_step(flip ? a->world_b_dev : a->world_a_dev, flip ? a->world_a_dev : a->world_b_dev,
+                                a->stable_dev, a->side, action, a->spawn, a->stable_max, a->dead_rule, a->empty,
+                                a->empty_min, a->masked_toggle, a->obs_mirror, a->result, seq, stream);
+    if (rc == 0 && a->flip_planes != nullptr) ++*a->flip_planes;
+    return rc;
 }

@@ -247,6 +247,19 @@ int cgl_sim_step(const uint32_t *world_in_dev, uint32_t *world_out_dev, int8_t *
                  int32_t action, int spawn, int stable_max, int dead_rule, int empty, int empty_min,
                  int masked_toggle, int8_t *obs_mirror, int32_t *result, uint32_t seq, cgl_stream_t stream);
 uint32_t cgl_sim_step_max_side(void);
+/* The same call for bindings: everything that stays the same from step to step lives in a struct the caller fills
+ * once.  The current world is in world_a_dev if *flip_planes is even, else in world_b_dev; the library steps into
+ * the other plane and increments *flip_planes (a host counter owned by the caller; NULL = always a -> b). */
+typedef struct cgl_sim_step_args {
+    uint32_t *world_a_dev, *world_b_dev;
+    int8_t *stable_dev;
+    uint32_t side;
+    int32_t spawn, stable_max, dead_rule, empty, empty_min, masked_toggle;
+    int8_t *obs_mirror;
+    int32_t *result;
+    uint32_t *flip_planes;
+} cgl_sim_step_args_t;
+int cgl_sim_step_ex(const cgl_sim_step_args_t *args, int32_t action, uint32_t seq, cgl_stream_t stream);
 
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
@@ -264,9 +277,11 @@ int cgl_life_step(const uint32_t *world_in_dev, uint32_t *world_out_dev, uint64_
                   cgl_stream_t stream);
 
 /* `gens` generations of ONE (rows x cols) grid, ping-ponging between buf_a (input) and buf_b,
- * `k` generations per launch kept in shared memory (temporal blocking; k = 1 streams).
- * *result_in_a_out = 1 if the final state is in buf_a else 0.  Requires cols % 128 == 0 for
- * the tiled kernels; other shapes fall back to cgl_life_step per generation. */
+ * `k` generations per HBM pass (temporal blocking in registers; k = 1 streams).  For k = 4, 8, 16 the bulk of the
+ * run is ONE cooperative launch in which a warp keeps its strip for all passes and waits only for its neighbour
+ * strips (cgl_life_persist.cu); otherwise one launch per pass, chained strip by strip.
+ * *result_in_a_out = 1 if the final state is in buf_a else 0.  The blocked kernels need cols % 32 == 0 and
+ * cols >= 960; other shapes fall back to cgl_life_step per generation. */
 int cgl_life_run(uint32_t *buf_a_dev, uint32_t *buf_b_dev, uint32_t rows, uint32_t cols,
                  int wrap_rows, uint32_t gens, uint32_t k, int *result_in_a_out,
                  cgl_stream_t stream);
@@ -333,6 +348,9 @@ int cgl_stream_wait(cgl_stream_t stream);
  *   planes           world_a_dev / world_b_dev / stable_dev: [n_groups * n_replicas] device pointers, index
  *                    group * n_replicas + replica; world_a holds the current world at creation.
  *   obs_host         NULL, or [n_groups] pinned int8 buffers of envs_per_group * side^2 bytes.
+ *   flags            CGL_ROLLOUT_ZERO_COPY_ACTIONS: no H2D copy node -- the kernel reads each env's action straight
+ *                    from the pinned, host-mapped action buffer over PCIe (one load per env, issued first thing by
+ *                    the env's CTA).  Takes the copy engine's latency out of every group step.
  * cgl_rollout_buffers: the group's pinned action (host writes) and reward (host reads) buffers, int32[envs_per_group];
  *                    actions start as side*side ("do nothing").
  * cgl_rollout_run:   `steps` steps of every group.  policy(user, group, step, reward_host, actions_host) may be NULL
@@ -341,9 +359,10 @@ int cgl_stream_wait(cgl_stream_t stream);
 typedef struct cgl_rollout cgl_rollout_t;
 typedef void (*cgl_policy_fn)(void *user, uint32_t group, uint64_t step, const int32_t *reward_host,
                               int32_t *actions_host);
+#define CGL_ROLLOUT_ZERO_COPY_ACTIONS 1u
 int cgl_rollout_create(cgl_rollout_t **out, uint32_t n_groups, uint32_t n_replicas, uint32_t *const *world_a_dev,
                        uint32_t *const *world_b_dev, int8_t *const *stable_dev, uint64_t envs_per_group,
-                       uint32_t side, int spawn, int stable_max, int8_t *const *obs_host);
+                       uint32_t side, int spawn, int stable_max, int8_t *const *obs_host, uint32_t flags);
 int cgl_rollout_buffers(cgl_rollout_t *r, uint32_t group, int32_t **actions_host, int32_t **reward_host);
 int cgl_rollout_run(cgl_rollout_t *r, uint64_t steps, cgl_policy_fn policy, void *user);
 int cgl_rollout_parity(const cgl_rollout_t *r, uint32_t group, uint32_t replica);
@@ -385,6 +404,29 @@ int cgl_life_band_block(const uint32_t *in_dev, uint32_t *out_dev, uint32_t buf_
                         uint32_t ghost, uint32_t gens, uint32_t *peer_up_out, uint32_t *peer_dn_out,
                         uint32_t *peer_up_ctr, uint32_t *peer_dn_ctr, const uint32_t *my_ctr,
                         uint32_t block_index, cgl_stream_t stream);
+
+/* Row-band run with the halo exchange INSIDE the kernel (the default multi-GPU path of life mode): n_sub sub-steps
+ * of k generations (k = 4, 8 or 16; ghost a multiple of k) over this rank's band buffers (ghost rows, owned rows,
+ * ghost rows; buf_a holds the current state, the result is in buf_a if n_sub is even, else in buf_b) in ONE
+ * cooperative launch -- a warp keeps its strip of rows for the whole call and waits only for its neighbour strips.
+ * Every ghost / k sub-steps (a "block") and after the last sub-step, the strips that own the first / last `ghost`
+ * owned rows store them into the ring neighbours' landing zones (peer_*_landing[slot], CUDA-IPC mapped, ghost x
+ * cols/32 words each, slot = block & 1) and bump their arrival counters (peer_*_ctr); at the start of a block the
+ * strips that read ghost rows wait on my_ctr_* and copy what they will read from my_landing_*[slot] into the
+ * band buffer.  Interior strips never wait for another GPU.
+ *   block_index   blocks (= pushes) consumed by earlier calls since the counters were zeroed; the caller adds
+ *                 ceil(n_sub / (ghost / k)) after each call.
+ *   initial_push  1 on a fresh grid (counters zeroed, block_index 0): the edge rows of buf_a are pushed before the
+ *                 first sub-step.  With n_sub = 0 the call only pushes.
+ * Bounded waits: a neighbour that never delivers raises alarm word 3, the kernel stores nothing further and ends.
+ * cgl_life_band_run_supported: 1 if a band of this shape fits a cooperative launch on the current device. */
+int cgl_life_band_run(uint32_t *buf_a_dev, uint32_t *buf_b_dev, uint32_t buf_rows, uint32_t cols, uint32_t ghost,
+                      uint32_t k, uint32_t n_sub, uint32_t block_index, int initial_push,
+                      uint32_t *const peer_up_landing[2], uint32_t *const peer_dn_landing[2], uint32_t *peer_up_ctr,
+                      uint32_t *peer_dn_ctr, const uint32_t *const my_landing_up[2],
+                      const uint32_t *const my_landing_dn[2], const uint32_t *my_ctr_up, const uint32_t *my_ctr_dn,
+                      cgl_stream_t stream);
+int cgl_life_band_run_supported(uint32_t buf_rows, uint32_t cols, uint32_t k);
 
 /* Plain cudaMalloc'ed (zero-filled) device memory: IPC handles need whole allocations, which
  * a caching allocator's sub-blocks are not. */
