@@ -25,7 +25,7 @@ Exchange back ends
           them straight into the neighbours' next input buffers over NVLink (CUDA-IPC mapped peer
           memory) and bump an arrival counter; only the strips that read ghost rows wait for the
           neighbours' previous block.  No exchange launches, no host sync, interior strips never wait.
-  "p2p"   (default on GPUs) one exchange launch per block (`cgl_halo_exchange`, 2 CTAs): writes the strip
+  "p2p"   (default on GPUs) one exchange launch per block (`cgl_halo_exchange`, 8 CTAs per neighbour): writes the strip
           straight into the neighbour's landing zone and publishes a sequence flag;
           `cgl_halo_wait_copy` on the neighbour spins on the flag and moves the strip into its
           ghost rows.  Two landing slots alternate by block parity, so a rank may run one block

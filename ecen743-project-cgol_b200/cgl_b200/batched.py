@@ -73,7 +73,7 @@ class BatchedSim:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_envs, self.side, self.size = n_envs, side, side * side
         self.W = (side + 31) // 32
-        self.seed, self.first_env = seed, first_env
+        self.seed, self.first_env, self.rng = seed, first_env, rng
         self.spawn, self.stable_max = spawnStabilityFactor, stableStabilityFactor
         self.count = 0
         self.max_steps = max_steps
@@ -403,28 +403,37 @@ class BatchedSim:
         stability plane and every constant needed to resume.  The per-env form in the reference's array format
         is sim.save() (CGL/CGL.py:332-333); this is the batched, 8x smaller form of the same state."""
         np.savez_compressed(
-            path, format=np.array("cgl_b200.batched.v1"), world=self._wa.cpu().numpy().view(np.uint32),
+            path, format=np.array("cgl_b200.batched.v2"), world=self._wa.cpu().numpy().view(np.uint32),
             stable=self.stable.cpu().numpy(), init_world=self._init_world.cpu().numpy().view(np.uint32),
-            init_stable=self._init_stable.cpu().numpy(),
+            init_stable=self._init_stable.cpu().numpy(), rng=np.array(self.rng),
             meta=np.array([self.n_envs, self.side, self.count, self.spawn, self.stable_max, DEAD_RULES[self.dead_rule],
-                           self.empty, self.empty_min, int(self.masked_toggle), self.seed, self.first_env], dtype=np.int64))
+                           self.empty, self.empty_min, int(self.masked_toggle), self.seed, self.first_env,
+                           -1 if self.max_steps is None else self.max_steps], dtype=np.int64))
 
     @classmethod
     def load_checkpoint(cls, path, device="cuda") -> "BatchedSim":
-        """Rebuild a BatchedSim from save_checkpoint(); stepping it continues bit for bit where the saved one was."""
+        """Rebuild a BatchedSim from save_checkpoint(); stepping it continues bit for bit where the saved one was
+        (planes, counters, `done` horizon and what reset() returns to)."""
         with np.load(path) as z:
-            if str(z["format"]) != "cgl_b200.batched.v1":
+            fmt = str(z["format"])
+            if fmt not in ("cgl_b200.batched.v1", "cgl_b200.batched.v2"):
                 raise ValueError(f"{path}: not a cgl_b200 batched checkpoint")
-            n, side, count, spawn, smax, rule, empty, emin, masked, seed, first = (int(v) for v in z["meta"])
+            meta = [int(v) for v in z["meta"]]
+            n, side, count, spawn, smax, rule, empty, emin, masked, seed, first = meta[:11]
+            max_steps = meta[11] if len(meta) > 11 and meta[11] >= 0 else None
+            rng = str(z["rng"]) if "rng" in z.files else "reference"
             world, stable = z["world"], z["stable"]
             init_world, init_stable = z["init_world"], z["init_stable"]
         W = (side + 31) // 32
-        if world.shape != (n, side, W) or stable.shape != (n, side * side):
-            raise ValueError(f"{path}: plane shapes do not match the recorded batch ({n} envs, side {side})")
+        for name, arr, shape in (("world", world, (n, side, W)), ("stable", stable, (n, side * side)),
+                                 ("init_world", init_world, (n, side, W)), ("init_stable", init_stable, (n, side * side))):
+            if arr.shape != shape:
+                raise ValueError(f"{path}: {name} has shape {arr.shape}, expected {shape} ({n} envs, side {side})")
         rule_name = {v: k for k, v in DEAD_RULES.items()}[rule]
         env = cls(n, side, seed=seed, spawnStabilityFactor=spawn, stableStabilityFactor=smax, device=device,
                   states=np.zeros((n, side * side), np.uint8), first_env=first, dead_rule=rule_name, empty=empty,
-                  empty_min=emin, masked_toggle=bool(masked))
+                  empty_min=emin, masked_toggle=bool(masked), max_steps=max_steps)
+        env.rng = rng
         env._wa.copy_(torch.from_numpy(world.view(np.int32)))
         env.stable.copy_(torch.from_numpy(stable))
         env._init_world.copy_(torch.from_numpy(init_world.view(np.int32)))

@@ -188,11 +188,11 @@ class BatchedDQNAgent:
         self.update_freq, self.batch_size = update_freq, batch_size
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed + 7919 * self.rank)
-        prev = torch.random.get_rng_state()
-        torch.manual_seed(seed)                                           # weight init, reproducible per seed
-        self.Q = QNetwork(self.state_dim, self.action_dim, hidden, self.device)
-        self.Q_target = QNetwork(self.state_dim, self.action_dim, hidden, self.device)
-        torch.random.set_rng_state(prev)
+        # weight init, reproducible per seed, without disturbing the caller's CPU or CUDA generators
+        with torch.random.fork_rng(devices=[self.device] if self.device.type == "cuda" else []):
+            torch.manual_seed(seed)
+            self.Q = QNetwork(self.state_dim, self.action_dim, hidden, self.device)
+            self.Q_target = QNetwork(self.state_dim, self.action_dim, hidden, self.device)
         # one multi-tensor launch per update on the GPU (same arithmetic as the reference's optim.Adam)
         self.optimizer = torch.optim.Adam(self.Q.parameters(), lr=self.lr, fused=self.device.type == "cuda")
         self.memory = TrajectoryReplay(env, max_size, batch_size, seed + 7919 * self.rank)

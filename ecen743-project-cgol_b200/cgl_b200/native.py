@@ -12,7 +12,7 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "libcgl_b200.so")
+LIB_PATH = os.environ.get("CGL_B200_LIB") or os.path.join(_PKG_DIR, "libcgl_b200.so")      # (override: tuning builds)
 
 E_BADARG, E_BADINDEX, E_NOMEM = -1, -2, -3
 

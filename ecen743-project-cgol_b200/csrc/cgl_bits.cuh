@@ -150,22 +150,25 @@ CGL_HD uint32_t dead_value4(int rule, uint32_t s, uint32_t min4, uint32_t empty4
     return 0u;
 }
 
-// The decay rule for 4 cells as ONE bytewise addition: every byte gets a delta of +1 (survivor below MAX), -1 = 0xFF
-// (dead cell above MIN) or 0, then born cells are overwritten with SPAWN.  The two "byte != constant" tests
-// leave their answer in bit 7 of each byte, already masked with the cell class; bit 7 -> delta runs on the FMA
-// pipe (IMAD.HI / IMAD), which the integer-pipe-bound kernel has to spare.
+// The decay rule for 4 cells as ONE equality test and ONE bytewise addition.  A cell is a survivor, dead or born;
+// survivors compare against MAX and add 1, dead cells compare against MIN and add -1, born cells are overwritten
+// with SPAWN at the end (whatever was computed for them).  So the constant a byte is compared with is SELECTED per
+// byte (one LOP3), the "byte != constant" test leaves its answer in bit 7, bit 7 -> 0x00 / 0xFF runs on the FMA pipe
+// (IMAD.HI / IMAD, which the integer-pipe-bound kernel has to spare) and one more LOP3 turns 0xFF into the delta
+// 0x01 for survivors.  11 integer-pipe operations per 4 cells (the two-test form it replaces took 16).
 CGL_HD uint32_t stable_update4_decay(uint32_t s, uint32_t surv_mask, uint32_t born_mask, uint32_t spawn4,
                                      uint32_t max4, uint32_t min4)
 {
     const uint32_t H = 0x80808080u, L = 0x7f7f7f7fu;
-    const uint32_t xa = s ^ max4, xb = s ^ min4;
-    const uint32_t inc7 = (((xa & L) + L) | xa) & (surv_mask & H);                  // bit 7: survivor and s != MAX
-    const uint32_t dec7 = (((xb & L) + L) | xb) & (~(surv_mask | born_mask) & H);   // bit 7: dead and s != MIN
+    const uint32_t cmp = (max4 & surv_mask) | (min4 & ~surv_mask);                  // per byte: MAX or MIN
+    const uint32_t x = s ^ cmp;
+    const uint32_t ne7 = (((x & L) + L) | x) & H;                                   // bit 7: s != its constant
 #if defined(__CUDA_ARCH__)
-    const uint32_t d = __umulhi(dec7, 1u << 25) * 255u + __umulhi(inc7, 1u << 25);  // bytes: 0xFF / 0x01 / 0x00
+    const uint32_t m = __umulhi(ne7, 1u << 25) * 255u;                              // bytes: 0xFF where it moves
 #else
-    const uint32_t d = (dec7 >> 7) * 255u + (inc7 >> 7);
+    const uint32_t m = (ne7 >> 7) * 255u;
 #endif
+    const uint32_t d = m & (~surv_mask | 0x01010101u);                              // +1 survivors, -1 (0xFF) dead
     const uint32_t sum = ((s & L) + (d & L)) ^ ((s ^ d) & H);                       // bytewise s + d, wraps like int8
     return (sum & ~born_mask) | (spawn4 & born_mask);
 }
@@ -176,6 +179,7 @@ CGL_HD uint32_t stable_update4_rule(int rule, uint32_t s, uint32_t surv_mask, ui
                                     uint32_t max4, uint32_t min4, uint32_t empty4)
 {
     if (rule == CGL_DEAD_DECAY) return stable_update4_decay(s, surv_mask, born_mask, spawn4, max4, min4);
+    // (the saturating rule as one merged addition + minimum was measured SLOWER than the two separate updates: 29.7 vs 28.8 us)
     const uint32_t live = (inc_unless_max4(s, max4) & surv_mask) | (spawn4 & born_mask);
     return live | (dead_value4(rule, s, min4, empty4) & ~(surv_mask | born_mask));
 }

@@ -441,7 +441,7 @@ def test_checkpoint_resume_continues_bit_for_bit(cgl, tmp_path, kw):
     from cgl_b200.batched import BatchedSim
     side = kw.pop("side")
     n, size = 40, side * side
-    env = BatchedSim(n, side, seed=6, spawnStabilityFactor=-2, stableStabilityFactor=2, rng="device", **kw)
+    env = BatchedSim(n, side, seed=6, spawnStabilityFactor=-2, stableStabilityFactor=2, rng="device", max_steps=6, **kw)
     g = torch.Generator(device="cuda"); g.manual_seed(2)
     acts = [torch.randint(0, size + 1, (n,), dtype=torch.int32, device="cuda", generator=g) for _ in range(8)]
     for a in acts[:3]:
@@ -451,10 +451,12 @@ def test_checkpoint_resume_continues_bit_for_bit(cgl, tmp_path, kw):
     twin = BatchedSim.load_checkpoint(path)
     assert twin.count == env.count == 3 and twin.dead_rule == env.dead_rule and twin.masked_toggle == env.masked_toggle
     assert torch.equal(twin.world, env.world) and torch.equal(twin.stable, env.stable)
+    assert twin.max_steps == 6 and twin.rng == "device"                     # (format v2: the `done` horizon travels too)
     for a in acts[3:]:
-        oa, ra, _ = env.step(a)
-        ob, rb, _ = twin.step(a)
+        oa, ra, da = env.step(a)
+        ob, rb, db = twin.step(a)
         assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(env.world, twin.world)
+        assert torch.equal(da, db) and bool(da.all()) == (env.count >= 6)
     env.reset(); twin.reset()
     assert torch.equal(env.world, twin.world) and torch.equal(env.stable, twin.stable)
     with pytest.raises(ValueError):
