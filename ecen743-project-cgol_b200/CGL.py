@@ -148,6 +148,31 @@ class sim:
         _say("CGL is now running...")
 
     # ------------------------------------------------------------------------------ internals
+    _serving = False                                        # a resident step server (cgl_sim_serve) may be alive
+    _bs = None
+
+    @property
+    def _b(self):
+        """The batched driver that owns the device planes.  Every path that lets OTHER kernels touch the planes goes
+        through this property, which first makes the resident step server hand the state back (no-op otherwise);
+        the step path itself uses `_bs`."""
+        if self._serving:
+            self._serve_stop()
+        return self._bs
+
+    @_b.setter
+    def _b(self, value):
+        if self._serving:
+            self._serve_stop()
+        self._bs = value
+
+    def __del__(self):
+        try:                                                # the server reads our pinned buffers: stop it before they go
+            if self._serving:
+                self._serve_stop()
+        except Exception:  # noqa: BLE001
+            pass
+
     def _env_variant(self):
         """Extra BatchedSim keywords; the CGL_action+ facade overrides this (dead-cell rule, masked toggle)."""
         return {}
@@ -172,16 +197,25 @@ class sim:
         self._world_live = self._stable_live = False       # a shallow view has been handed out
         # result block of the one-launch step (cgl_sim_step): the kernel writes reward, live count and then the
         # step's sequence number into this pinned, host-mapped memory; the host polls the sequence word
-        self._res_t = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._res_t = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._res = self._res_t.numpy()
         self._seq = 0
+        # resident step server (cgl_sim_serve): the host posts (seq << 32) | action into this pinned word and the
+        # kernel answers in the result block; _res[4] == _launch_id means that launch has left
+        self._cmd_t = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self._cmd = self._cmd_t.numpy().view(np.uint64)
+        self._launch_id = 0
+        self._serve_stream = None
         self._pending_seq = None                            # sequence number of a step whose results are in flight
         self._pending = None                                # scalar toggle deferred into the next step()
         self._lazy_steps = 0                                # plain steps not yet executed (see step())
         self._reward_valid = False                          # _res[0] holds reward() of the current state
         self._alive_valid = False                           # _res[1] holds alive() of the current state
-        self._fast = self.side <= int(self._b._lib.cgl_sim_step_max_side())
+        lib = self._bs._lib
+        self._fast = self.side <= int(lib.cgl_sim_step_max_side())
         self._fast_args = {}
+        self._linger_us = max(0, min(100000, int(os.environ.get("CGL_SIM_LINGER_US", "250"))))
+        self._serve_ok = self._fast and self._linger_us > 0 and self.side <= int(lib.cgl_sim_serve_max_side())
 
     def _invalidate(self):
         """The state changed by something other than a step: cached reward / live count are stale."""
@@ -193,14 +227,84 @@ class sim:
         seq = self._pending_seq
         if seq is None:
             return
-        res, spins = self._res, 0
-        while res[2] != seq:
-            spins += 1
-            if spins > 200000:                              # ~50 ms: something is wrong, let CUDA report it
-                self._torch.cuda.current_stream(self._dev).synchronize()
-                if res[2] != seq:
-                    raise RuntimeError("CGL.sim: the step kernel finished without delivering its results")
+        res = self._res
+        if res[2] != seq:
+            spins = 0
+            while res[2] != seq:
+                spins += 1
+                if self._serving:
+                    if res[4] == self._launch_id:           # the server has left (idle for too long) ...
+                        if res[2] != seq:                   # ... before it saw this command: launch it again
+                            self._serve_launch((seq - 1) & 0x3fffffff)
+                    elif spins > 4000000:
+                        self._serve_stream.synchronize()
+                        raise RuntimeError("CGL.sim: the resident step kernel does not answer")
+                elif spins > 200000:                        # ~50 ms: something is wrong, let CUDA report it
+                    self._torch.cuda.current_stream(self._dev).synchronize()
+                    if res[2] != seq:
+                        raise RuntimeError("CGL.sim: the step kernel finished without delivering its results")
         self._pending_seq = None
+
+    def _step_args(self):
+        """The cached cgl_sim_step_args_t of this env (constants and pointers; rebuilt after load())."""
+        args = self._fast_args.get("args")
+        if args is None:
+            import ctypes
+            from cgl_b200 import native
+            from cgl_b200.batched import DEAD_RULES
+            b = self._bs
+            st = native.SimStepArgs()
+            st.world_a, st.world_b, st.stable = b._wa.data_ptr(), b._wb.data_ptr(), b.stable.data_ptr()
+            st.side, st.spawn, st.stable_max = self.side, b.spawn, b.stable_max
+            st.dead_rule, st.empty, st.empty_min = DEAD_RULES[b.dead_rule], b.empty, b.empty_min
+            st.masked_toggle = int(b.masked_toggle)
+            st.obs_mirror, st.result = self._m_stable_t.data_ptr(), self._res_t.data_ptr()
+            flip = ctypes.c_uint32(0)                        # even: the world is in the plane that is `world_a` here
+            st.flip_planes = ctypes.pointer(flip)
+            raw = getattr(self._torch._C, "_cuda_getCurrentRawStream", None)
+            args = (st, ctypes.byref(st), flip, b._lib.cgl_sim_step_ex, raw, self._dev.index, b._wa.data_ptr(),
+                    b._lib.cgl_sim_serve, self._cmd_t.data_ptr())
+            self._fast_args["args"] = args
+        # the planes this struct was built from may have been swapped by other calls (run, batched step, ...)
+        want_odd = self._bs._wa.data_ptr() != args[6]
+        if bool(args[2].value & 1) != want_odd:
+            args[2].value = int(want_odd)
+        return args
+
+    def _serve_launch(self, last_seq):
+        """(Re)launch the resident step server on its own non-blocking stream, ordered after whatever the current
+        stream still has queued on the planes."""
+        torch = self._torch
+        args = self._step_args()
+        with torch.cuda.device(self._dev):
+            if self._serve_stream is None:
+                self._serve_stream = torch.cuda.Stream(device=self._dev)
+            self._serve_stream.wait_stream(torch.cuda.current_stream(self._dev))
+            self._launch_id = lid = self._launch_id % 0x3fffffff + 1
+            rc = args[7](args[1], args[8], last_seq, lid, self._linger_us, self._serve_stream.cuda_stream)
+        if rc:
+            from cgl_b200 import native
+            native.check(rc, "cgl_sim_serve")
+        self._bs.launches += 1
+        self._serving = True
+
+    def _serve_stop(self):
+        """Make the resident server write the planes back and leave; afterwards the device planes are current."""
+        if not self._serving:
+            return
+        self._wait()
+        res, lid = self._res, self._launch_id
+        if res[4] != lid:
+            self._seq = seq = (self._seq + 1) & 0x3fffffff
+            self._cmd[0] = (seq << 32) | 0xFFFFFFFE          # CGL_SIM_QUIT
+            spins = 0
+            while res[4] != lid:
+                spins += 1
+                if spins > 4000000:
+                    self._serve_stream.synchronize()
+                    if res[4] != lid:
+                        raise RuntimeError("CGL.sim: the resident step kernel did not leave")
+        self._serving = False
 
     def _flush(self):
         """Bring the device state up to date with everything the caller has asked for so far: run the plain
@@ -294,52 +398,44 @@ class sim:
             self._invalidate()
             self._world_fresh = self._stable_fresh = False
             return
-        self._run_lazy()
+        if self._lazy_steps:
+            self._run_lazy()
         self._step_now()
 
     def _step_now(self):
-        """toggle (if one is pending) + generation + stability + reward + live count in ONE launch
-        (cgl_sim_step): the action travels by value, the new observation is stored by the kernel into the pinned
-        mirror as well, and reward / live count / sequence number into the pinned result block."""
+        """toggle (if one is pending) + generation + stability + reward + live count.  Sides the resident server
+        takes (cgl_sim_serve): the action is posted into a pinned command word and a kernel that keeps the env on
+        chip answers -- no launch per step.  Otherwise ONE launch (cgl_sim_step): the action travels by value.
+        Either way the new observation is stored by the kernel into the pinned mirror and reward / live count /
+        sequence number into the pinned result block."""
         a = self.size                                       # "do nothing"
         if self._pending is not None:
             a, self._pending = self._pending, None
-        b = self._b
         if not self._fast:
             return self._step_now_batched(a)
-        args = self._fast_args.get("args")
-        if args is None:
-            import ctypes
-            from cgl_b200 import native
-            from cgl_b200.batched import DEAD_RULES
-            st = native.SimStepArgs()
-            st.world_a, st.world_b, st.stable = b._wa.data_ptr(), b._wb.data_ptr(), b.stable.data_ptr()
-            st.side, st.spawn, st.stable_max = self.side, b.spawn, b.stable_max
-            st.dead_rule, st.empty, st.empty_min = DEAD_RULES[b.dead_rule], b.empty, b.empty_min
-            st.masked_toggle = int(b.masked_toggle)
-            st.obs_mirror, st.result = self._m_stable_t.data_ptr(), self._res_t.data_ptr()
-            flip = ctypes.c_uint32(0)                        # even: the world is in the plane that is `world_a` here
-            st.flip_planes = ctypes.pointer(flip)
-            raw = getattr(self._torch._C, "_cuda_getCurrentRawStream", None)
-            args = (st, ctypes.byref(st), flip, b._lib.cgl_sim_step_ex, raw, self._dev.index, b._wa.data_ptr())
-            self._fast_args["args"] = args
-        # the planes this struct was built from may have been swapped by other calls (run, batched step, ...)
-        want_odd = b._wa.data_ptr() != args[6]
-        if bool(args[2].value & 1) != want_odd:
-            args[2].value = int(want_odd)
-        self._wait()                                        # one step in flight at a time (the result block is shared)
+        b = self._bs
+        if self._pending_seq is not None:
+            self._wait()                                    # one step in flight at a time (the result block is shared)
         self._seq = seq = (self._seq + 1) & 0x3fffffff
-        torch = self._torch
-        if torch.cuda.current_device() != self._dev.index:
-            torch.cuda.set_device(self._dev)
-        stream = args[4](args[5]) if args[4] is not None else torch.cuda.current_stream(self._dev).cuda_stream
-        rc = args[3](args[1], a, seq, stream)
-        if rc:
-            from cgl_b200 import native
-            native.check(rc, "cgl_sim_step")
-        b._wa, b._wb = b._wb, b._wa
+        if self._serve_ok and not self._world_live:
+            self._cmd[0] = (seq << 32) | a
+            if not self._serving or self._res[4] == self._launch_id:
+                self._serve_launch((seq - 1) & 0x3fffffff)
+        else:
+            if self._serving:
+                self._serve_stop()
+            args = self._step_args()
+            torch = self._torch
+            if torch.cuda.current_device() != self._dev.index:
+                torch.cuda.set_device(self._dev)
+            stream = args[4](args[5]) if args[4] is not None else torch.cuda.current_stream(self._dev).cuda_stream
+            rc = args[3](args[1], a, seq, stream)
+            if rc:
+                from cgl_b200 import native
+                native.check(rc, "cgl_sim_step")
+            b._wa, b._wb = b._wb, b._wa
+            b.launches += 1
         b.count += 1
-        b.launches += 1
         self._pending_seq = seq
         self._reward_valid = self._alive_valid = True
         self._stable_fresh = True                           # valid once _wait() has seen the sequence number
@@ -361,7 +457,7 @@ class sim:
 
     @property
     def _can_defer(self):
-        return self._b.fused or self.side <= 273            # sides cgl_env_run can keep on chip
+        return self._bs.fused or self.side <= 273           # sides cgl_env_run can keep on chip
 
     # ---- extensions (not in CGL/CGL.py): the reference's own loops around step(), run on the device ----
     def run(self, iters, until_fixed=False):
@@ -395,9 +491,11 @@ class sim:
 
     def reward(self):
         """np.int32 sum of the stability vector (CGL/CGL.py:255-256)."""
-        self._flush()
+        if self._lazy_steps or self._pending is not None:
+            self._flush()
         if self._reward_valid:                              # written by the last step's kernel
-            self._wait()
+            if self._pending_seq is not None:
+                self._wait()
             return np.int32(self._res[0])
         return np.int32(self._b.reward().item())
 
@@ -440,10 +538,16 @@ class sim:
 
     def get_stable(self, vector=False, shallow=False):
         """Stability (the observation) as int8 vector or matrix (CGL/CGL.py:281-285)."""
-        self._flush()
+        if self._lazy_steps or self._pending is not None:
+            self._flush()
         if shallow:
             self._stable_live = True
-        s = self._sync_stable()
+        if self._stable_fresh:                              # the step's kernel wrote the mirror itself
+            if self._pending_seq is not None:
+                self._wait()
+            s = self._m_stable
+        else:
+            s = self._sync_stable()
         out = s if vector else s.reshape((self.side, self.side))
         return out if shallow else np.copy(out)
 
@@ -488,9 +592,10 @@ class sim:
             # the only place it is not yet visible is a shallow numpy view read before the next call.
             a = int(indx)
             if 0 <= a < self.size:
-                self._flush()                               # an earlier deferred toggle goes first
+                if self._lazy_steps or self._pending is not None:
+                    self._flush()                           # an earlier deferred toggle goes first
                 self._pending = a
-                self._invalidate()
+                self._reward_valid = self._alive_valid = False
             elif a != self.size:
                 raise ValueError("Not all indexes are valid!\nIndexes must be positive and less than the size of the "
                                  f"state {self.size}.")

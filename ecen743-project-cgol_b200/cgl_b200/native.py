@@ -99,6 +99,9 @@ class SimStepArgs(ctypes.Structure):
 
 
 SIGNATURES["cgl_sim_step_ex"] = (_i, [ctypes.POINTER(SimStepArgs), ctypes.c_int32, _u32, _vp])
+SIGNATURES["cgl_sim_serve"] = (_i, [ctypes.POINTER(SimStepArgs), _vp, _u32, _u32, _u32, _vp])
+SIGNATURES["cgl_sim_serve_max_side"] = (_u32, [])
+SIM_QUIT = 0xFFFFFFFE
 
 POLICY_FN = ctypes.CFUNCTYPE(None, _vp, _u32, _u64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32))
 SIGNATURES["cgl_rollout_create"] = (_i, [ctypes.POINTER(_vp), _u32, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp),

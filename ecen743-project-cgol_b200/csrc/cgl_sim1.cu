@@ -123,6 +123,160 @@ sim1_step_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ w
     }
 }
 
+
+// ---- the resident form: the environment stays on chip BETWEEN steps -----------------------------------------
+// A launch per step costs the facade ~9 us of launch latency for ~1 us of work.  sim1_serve_kernel is launched once,
+// keeps the world (one byte per cell, two planes) and the stability plane in shared memory, and then serves steps:
+// thread 0 polls a 64-bit command word in pinned host memory ((seq << 32) | action, written by the host with one
+// store), the CTA performs toggle + generation + stability + reward, stores the new observation into the caller's
+// pinned mirror and publishes {reward, alive, seq} with ONE 16-byte store the host polls.  No launch, no copy, no
+// stream synchronisation per step.  The kernel LEAVES -- device planes written back, result[4] = launch_id -- when
+// the host sends SIM1_QUIT or when no command arrived for `linger_ns`: a host that goes away to do other work (a
+// Q-network update, a device-wide synchronise) is never blocked for longer than that, and its next step simply
+// launches the kernel again.
+constexpr uint32_t SIM1_SERVE_MAX_SIDE = 256;    // 3 x side^2 bytes of shared memory
+constexpr uint32_t SIM1_QUIT = 0xFFFFFFFEu;
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, int8_t spawn, int8_t stable_max,
+                  int rule, int8_t empty, int8_t empty_min, int masked, int8_t *obs_mirror, int32_t *result,
+                  const unsigned long long *cmd, uint32_t last_seq, uint32_t launch_id, unsigned long long linger_ns,
+                  uint32_t tpr, uint32_t rows_per_pass)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const uint32_t size = side * side, n_words = side * W, pad = (size + 15u) & ~15u;
+    uint8_t *cur = smem_dyn, *nxt = smem_dyn + pad;               // world planes, one byte per cell
+    int8_t *stab = reinterpret_cast<int8_t *>(smem_dyn + 2 * pad);
+    __shared__ int red[2];
+    __shared__ uint32_t bc[2];
+    const uint32_t ty = threadIdx.x / tpr, x0 = (threadIdx.x - ty * tpr) * 4;
+    const bool lane_ok = ty < rows_per_pass;
+    const uint32_t nx = side - x0 < 4 ? side - x0 : 4;
+    const bool vec = (side & 3u) == 0;
+
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) {
+        const uint32_t y = i / side, x = i - y * side;
+        cur[i] = (uint8_t)((world[y * W + (x >> 5)] >> (x & 31)) & 1u);
+        stab[i] = stable[i];
+    }
+    uint32_t done = last_seq;
+    __syncthreads();
+
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned long long c;
+            for (;;) {
+                c = ld_sys_u64(cmd);
+                if ((uint32_t)(c >> 32) != done) break;
+                if (globaltimer_ns() - t0 > linger_ns) { c = SIM1_QUIT; break; }
+            }
+            const uint32_t action = (uint32_t)c;
+            if (action < size) {                                   // toggle_state before the step
+                const uint8_t v = cur[action] ^ 1u;
+                cur[action] = v;
+                stab[action] = (masked && !v) ? (int8_t)0 : spawn;
+            }
+            bc[0] = action;
+            bc[1] = (uint32_t)(c >> 32);
+            red[0] = 0;
+            red[1] = 0;
+        }
+        __syncthreads();
+        if (bc[0] == SIM1_QUIT) break;
+        done = bc[1];
+
+        int acc = 0;
+        uint32_t pop = 0;
+        if (lane_ok)
+            for (uint32_t y = ty; y < side; y += rows_per_pass) {
+                const uint32_t yu = (y == 0 ? side : y) - 1, yd = (y + 1 == side) ? 0 : y + 1;
+                const uint8_t *ru = cur + yu * side, *rc = cur + y * side, *rd = cur + yd * side;
+                const uint32_t base = y * side + x0;
+                uint32_t sv = 0;
+                if (vec) sv = *reinterpret_cast<const uint32_t *>(stab + base);
+                else for (uint32_t k = 0; k < nx; ++k) sv |= (uint32_t)(uint8_t)stab[base + k] << (8 * k);
+                uint32_t col3[6], mid[6];
+#pragma unroll
+                for (uint32_t k = 0; k < 6; ++k) {
+                    if (k >= nx + 2) break;
+                    uint32_t x = x0 + k;                           // column x - 1 on the torus
+                    x = x == 0 ? side - 1 : (x - 1 >= side ? x - 1 - side : x - 1);
+                    mid[k] = rc[x];
+                    col3[k] = ru[x] + mid[k] + rd[x];
+                }
+                uint32_t out = 0, nbytes = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    if (k >= nx) break;
+                    const uint32_t p = mid[k + 1];
+                    const uint32_t cnt = col3[k] + col3[k + 1] + col3[k + 2] - p;
+                    const uint32_t q = (cnt == 3u) || (cnt == 2u && p);
+                    nbytes |= q << (8 * k);
+                    pop += q;
+                    int8_t s = (int8_t)(sv >> (8 * k));
+                    s = stable_update1_rule(rule, s, p != 0, q != 0, spawn, stable_max, empty, empty_min);
+                    acc += s;
+                    out |= (uint32_t)(uint8_t)s << (8 * k);
+                }
+                if (vec) {
+                    *reinterpret_cast<uint32_t *>(nxt + base) = nbytes;
+                    *reinterpret_cast<uint32_t *>(stab + base) = out;
+                } else {
+                    for (uint32_t k = 0; k < nx; ++k) {
+                        nxt[base + k] = (uint8_t)(nbytes >> (8 * k));
+                        stab[base + k] = (int8_t)(out >> (8 * k));
+                    }
+                }
+            }
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        pop = __reduce_add_sync(0xffffffffu, pop);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&red[0], acc);
+            atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
+        }
+        __syncthreads();
+        // the observation: shared memory -> the caller's pinned mirror (16-byte posted writes), fenced by the writers
+        if (obs_mirror != nullptr) {
+            const uint32_t n16 = size >> 4;
+            bool stored = false;
+            for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
+                reinterpret_cast<uint4 *>(obs_mirror)[i] = reinterpret_cast<const uint4 *>(stab)[i];
+                stored = true;
+            }
+            for (uint32_t i = (n16 << 4) + threadIdx.x; i < size; i += blockDim.x) {
+                obs_mirror[i] = stab[i];
+                stored = true;
+            }
+            if (stored) __threadfence_system();
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)                                      // one 16-byte store: reward, alive and seq arrive together
+            asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(result), "r"(red[0]), "r"(red[1]),
+                         "r"((int)done), "r"(0) : "memory");
+        uint8_t *t = cur; cur = nxt; nxt = t;
+    }
+
+    // leave: the device planes get the current state back, then the host is told
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
+        const uint32_t y = i / W, xw = (i - y * W) * 32;
+        uint32_t word = 0;
+        for (uint32_t j = 0; j < 32 && xw + j < side; ++j) word |= (uint32_t)cur[y * side + xw + j] << j;
+        world[i] = word;
+    }
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) stable[i] = stab[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int32_t *>(result + 4) = (int32_t)launch_id;
+}
+
 }  // namespace cgl
 
 using namespace cgl;
@@ -170,4 +324,37 @@ extern "C" int cgl_sim_step_ex(const cgl_sim_step_args_t *a, int32_t action, uin
                                 a->empty_min, a->masked_toggle, a->obs_mirror, a->result, seq, stream);
     if (rc == 0 && a->flip_planes != nullptr) ++*a->flip_planes;
     return rc;
+}
+
+extern "C" uint32_t cgl_sim_serve_max_side(void) { return SIM1_SERVE_MAX_SIDE; }
+
+// Launch the resident server for one environment (see sim1_serve_kernel).  The world plane that holds the state
+// (world_a if *flip_planes is even, else world_b) and the stability plane are read now and written back when the
+// kernel leaves; flip_planes is not advanced.
+extern "C" int cgl_sim_serve(const cgl_sim_step_args_t *a, const void *cmd_host, uint32_t last_seq, uint32_t launch_id,
+                             uint32_t linger_us, cgl_stream_t stream)
+{
+    CGL_REQUIRE(a && cmd_host && a->world_a_dev && a->world_b_dev && a->stable_dev && a->result && a->side,
+                CGL_E_BADARG, "cgl_sim_serve: bad argument");
+    CGL_REQUIRE(a->side <= SIM1_SERVE_MAX_SIDE, CGL_E_BADARG, "cgl_sim_serve: side must be <= %u", SIM1_SERVE_MAX_SIDE);
+    CGL_REQUIRE(a->dead_rule >= CGL_DEAD_ZERO && a->dead_rule <= CGL_DEAD_SAT && a->empty >= -128 && a->empty <= 127 &&
+                    a->empty_min >= -128 && a->empty_min <= 127 && linger_us > 0 && linger_us <= 100000,
+                CGL_E_BADARG, "cgl_sim_serve: dead_rule must be 0..2, empty / empty_min must fit int8, linger 1..100000 us");
+    static PerDeviceOnce once;
+    if (once.first())
+        CGL_CUDA(cudaFuncSetAttribute(sim1_serve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      3 * SIM1_SERVE_MAX_SIDE * SIM1_SERVE_MAX_SIDE));
+    const uint32_t side = a->side, size = side * side;
+    const uint32_t W = cgl_words_per_row(side), tpr = (side + 3) / 4;
+    uint32_t rows_per_pass = 1024 / tpr;
+    if (rows_per_pass > side) rows_per_pass = side;
+    const unsigned threads = (tpr * rows_per_pass + 31) / 32 * 32;
+    const size_t smem = 3 * (size_t)((size + 15u) & ~15u);
+    const bool flip = (a->flip_planes != nullptr) && (*a->flip_planes & 1u);
+    sim1_serve_kernel<<<1, threads, smem, as_stream(stream)>>>(
+        flip ? a->world_b_dev : a->world_a_dev, a->stable_dev, side, W, (int8_t)a->spawn, (int8_t)a->stable_max,
+        a->dead_rule, (int8_t)a->empty, (int8_t)a->empty_min, a->masked_toggle, a->obs_mirror, a->result,
+        static_cast<const unsigned long long *>(cmd_host), last_seq, launch_id, 1000ull * linger_us, tpr, rows_per_pass);
+    CGL_LAUNCH_CHECK();
+    return 0;
 }

@@ -261,6 +261,26 @@ typedef struct cgl_sim_step_args {
 } cgl_sim_step_args_t;
 int cgl_sim_step_ex(const cgl_sim_step_args_t *args, int32_t action, uint32_t seq, cgl_stream_t stream);
 
+/* The resident form of cgl_sim_step for the same loop (CGL/main.py:64-72) when the caller steps ONE environment over
+ * and over: cgl_sim_serve launches a single-CTA kernel that keeps the environment in shared memory and serves steps
+ * without any further launch, copy or stream synchronisation.
+ *   cmd_host      pinned host-mapped uint64 the host writes with one store: (seq << 32) | action, action as in
+ *                 cgl_sim_step, or CGL_SIM_QUIT to make the kernel leave.  A command is new when its seq differs
+ *                 from the last one served (`last_seq` at launch).
+ *   args->result  pinned host-mapped int32[8]: per served step ONE 16-byte store {reward, live cells, seq, 0}
+ *                 after the new observation is complete in args->obs_mirror (system-scope fence in between); when
+ *                 the kernel has left -- planes written back to world_a/world_b (whichever held the state, see
+ *                 flip_planes; not advanced) and stable_dev -- result[4] = launch_id.
+ *   linger_us     the kernel also leaves by itself after this long without a new command (1..100000), so a device-
+ *                 wide synchronisation elsewhere in the process is never held up for longer; the host notices
+ *                 result[4] == launch_id and launches again with the next step.
+ * `stream` must not be synchronised with by the host while commands are outstanding (use a non-blocking stream of
+ * its own).  Sides up to cgl_sim_serve_max_side(). */
+#define CGL_SIM_QUIT 0xFFFFFFFEu
+int cgl_sim_serve(const cgl_sim_step_args_t *args, const void *cmd_host, uint32_t last_seq, uint32_t launch_id,
+                  uint32_t linger_us, cgl_stream_t stream);
+uint32_t cgl_sim_serve_max_side(void);
+
 /* Which path cgl_env_step takes for `side`: 1 = fused fast kernel, 0 = generic kernels. */
 int cgl_env_step_is_fused(uint32_t side);
 
