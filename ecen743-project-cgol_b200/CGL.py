@@ -59,6 +59,9 @@ def _check_int8(name, v):
         raise OverflowError(f"Python integer {v} out of bounds for int8 ({name})")
 
 
+_NP_INT_TYPES = frozenset((np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.intp))
+
+
 class sim:
     """Conway's Game of Life environment with a per-cell int8 stability counter.
 
@@ -204,6 +207,9 @@ class sim:
         # kernel answers in the result block; _res[4] == _launch_id means that launch has left
         self._cmd_t = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._cmd = self._cmd_t.numpy().view(np.uint64)
+        # the hot loop reads and writes single words of these blocks: memoryviews hand out plain Python ints
+        self._res_w = memoryview(self._res)
+        self._cmd_w = memoryview(self._cmd)
         self._launch_id = 0
         self._serve_stream = None
         self._pending_seq = None                            # sequence number of a step whose results are in flight
@@ -227,7 +233,7 @@ class sim:
         seq = self._pending_seq
         if seq is None:
             return
-        res = self._res
+        res = self._res_w
         if res[2] != seq:
             spins = 0
             while res[2] != seq:
@@ -293,10 +299,10 @@ class sim:
         if not self._serving:
             return
         self._wait()
-        res, lid = self._res, self._launch_id
+        res, lid = self._res_w, self._launch_id
         if res[4] != lid:
             self._seq = seq = (self._seq + 1) & 0x3fffffff
-            self._cmd[0] = (seq << 32) | 0xFFFFFFFE          # CGL_SIM_QUIT
+            self._cmd_w[0] = (seq << 32) | 0xFFFFFFFE        # CGL_SIM_QUIT
             spins = 0
             while res[4] != lid:
                 spins += 1
@@ -400,6 +406,28 @@ class sim:
             return
         if self._lazy_steps:
             self._run_lazy()
+        if self._serving and self._pending_seq is None and not self._world_live:
+            # the DQN loop's step on the resident server, inlined (_step_now is the general form): post the command,
+            # mark what the kernel is about to deliver, wait for the answer if a live view has to show it
+            a = self._pending
+            if a is None:
+                a = self.size
+            else:
+                self._pending = None
+            self._seq = seq = (self._seq + 1) & 0x3fffffff
+            res = self._res_w
+            self._cmd_w[0] = (seq << 32) | a
+            if res[4] == self._launch_id:                   # it has left in the meantime (idle): launch it again
+                self._serve_launch((seq - 1) & 0x3fffffff)
+            self._bs.count += 1
+            self._reward_valid = self._alive_valid = self._stable_fresh = True
+            self._world_fresh = False
+            if self._stable_live and res[2] == seq:
+                return
+            self._pending_seq = seq
+            if self._stable_live:
+                self._wait()
+            return
         self._step_now()
 
     def _step_now(self):
@@ -418,8 +446,8 @@ class sim:
             self._wait()                                    # one step in flight at a time (the result block is shared)
         self._seq = seq = (self._seq + 1) & 0x3fffffff
         if self._serve_ok and not self._world_live:
-            self._cmd[0] = (seq << 32) | a
-            if not self._serving or self._res[4] == self._launch_id:
+            self._cmd_w[0] = (seq << 32) | a
+            if not self._serving or self._res_w[4] == self._launch_id:
                 self._serve_launch((seq - 1) & 0x3fffffff)
         else:
             if self._serving:
@@ -496,7 +524,7 @@ class sim:
         if self._reward_valid:                              # written by the last step's kernel
             if self._pending_seq is not None:
                 self._wait()
-            return np.int32(self._res[0])
+            return self._res[0]                            # (indexing the int32 block yields an np.int32)
         return np.int32(self._b.reward().item())
 
     def alive(self):
@@ -586,7 +614,8 @@ class sim:
         """Toggle the listed cells and set their stability to spawn (CGL/CGL.py:322-328).
         Duplicates toggle once; the scalar `size` is the silent "do nothing"; anything else out of
         range raises ValueError."""
-        if isinstance(indx, (int, np.integer)) and not isinstance(indx, bool):
+        t = type(indx)
+        if t is int or t in _NP_INT_TYPES or (isinstance(indx, (int, np.integer)) and not isinstance(indx, bool)):
             # the DQN loop's case (CGL/main.py:66-67): one index, then step().  The toggle is deferred and
             # travels by value into that launch.  Every other call into the env applies it first (_flush), so
             # the only place it is not yet visible is a shallow numpy view read before the next call.

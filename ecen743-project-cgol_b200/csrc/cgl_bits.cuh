@@ -305,6 +305,19 @@ CGL_HD void stable_update_sliced_decay(uint32_t (&p)[8], uint32_t surv, uint32_t
     }
 }
 
+// B3/S23 for FOUR cells held one per byte (values 0/1): u, m, d are the words of the row above, the cells' own row
+// and the row below; lc / rc the sums (0..3) of the three cells in the column left of byte 0 / right of byte 3.
+// Packed-byte arithmetic: column sums, then the 3x3 sum INCLUDING the cell (<= 9, no carry between bytes), then
+// alive next <=> sum == 3, or sum == 4 and alive now.  Returns 0/1 per byte.  (The single-env server, cgl_sim1.cu.)
+CGL_HD uint32_t life_next4_bytes(uint32_t u, uint32_t m, uint32_t d, uint32_t lc, uint32_t rc)
+{
+    const uint32_t col = u + m + d;
+    const uint32_t t = col + ((col << 8) | lc) + ((col >> 8) | (rc << 24));
+    const uint32_t ne3 = ((t ^ 0x03030303u) + 0x7f7f7f7fu) & 0x80808080u;           // bit 7 set: sum != 3
+    const uint32_t ne4 = ((t ^ 0x04040404u) + 0x7f7f7f7fu) & 0x80808080u;
+    return ((~ne3 >> 7) | ((~ne4 >> 7) & m)) & 0x01010101u;
+}
+
 // Expand a 4-bit nibble to 4 byte masks (bit i -> byte i = 0xFF).
 CGL_HD uint32_t nibble_to_bytemask(uint32_t nib)
 {

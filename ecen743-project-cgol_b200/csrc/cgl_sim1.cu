@@ -134,7 +134,7 @@ sim1_step_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ w
 // the host sends SIM1_QUIT or when no command arrived for `linger_ns`: a host that goes away to do other work (a
 // Q-network update, a device-wide synchronise) is never blocked for longer than that, and its next step simply
 // launches the kernel again.
-constexpr uint32_t SIM1_SERVE_MAX_SIDE = 256;    // 3 x side^2 bytes of shared memory
+constexpr uint32_t SIM1_SERVE_MAX_SIDE = 256;    // two halo'd byte planes + the stability plane: 197 KB of shared memory
 constexpr uint32_t SIM1_QUIT = 0xFFFFFFFEu;
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
@@ -144,6 +144,25 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
+// Shared-memory layout of a world plane: one byte per cell WITH torus halos, so that a thread's four cells and
+// their neighbours are three aligned 32-bit words plus six bytes and the neighbour count is packed-byte arithmetic
+// (no wrap logic, any side).  Row r (-1 .. side) starts at (r + 1) * stride; cell x sits at byte 4 + x, the left halo
+// (= cell side-1) at byte 3, the right halo (= cell 0) at byte 4 + side; every other byte of a row stays 0.
+__device__ __forceinline__ uint32_t serve_stride(uint32_t side) { return (side + 5u + 3u) & ~3u; }
+
+// Write one cell and every halo image of it.
+__device__ __forceinline__ void serve_set_cell(uint8_t *pl, uint32_t side, uint32_t S, uint32_t y, uint32_t x, uint8_t v)
+{
+    for (int ri = 0; ri < 3; ++ri) {
+        if (ri == 1 && y != 0) continue;                  // image in the bottom halo row
+        if (ri == 2 && y != side - 1) continue;           // image in the top halo row
+        uint8_t *row = pl + (ri == 0 ? y + 1 : (ri == 1 ? side + 1 : 0)) * S;
+        row[4 + x] = v;
+        if (x == 0) row[4 + side] = v;
+        if (x == side - 1) row[3] = v;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, int8_t spawn, int8_t stable_max,
                   int rule, int8_t empty, int8_t empty_min, int masked, int8_t *obs_mirror, int32_t *result,
@@ -151,21 +170,28 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
                   uint32_t tpr, uint32_t rows_per_pass)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    const uint32_t size = side * side, n_words = side * W, pad = (size + 15u) & ~15u;
-    uint8_t *cur = smem_dyn, *nxt = smem_dyn + pad;               // world planes, one byte per cell
-    int8_t *stab = reinterpret_cast<int8_t *>(smem_dyn + 2 * pad);
+    const uint32_t size = side * side, n_words = side * W, S = serve_stride(side);
+    const uint32_t plane_bytes = ((side + 2) * S + 15u) & ~15u;
+    uint8_t *cur = smem_dyn, *nxt = smem_dyn + plane_bytes;
+    int8_t *stab = reinterpret_cast<int8_t *>(smem_dyn + 2 * plane_bytes);
     __shared__ int red[2];
     __shared__ uint32_t bc[2];
     const uint32_t ty = threadIdx.x / tpr, x0 = (threadIdx.x - ty * tpr) * 4;
     const bool lane_ok = ty < rows_per_pass;
     const uint32_t nx = side - x0 < 4 ? side - x0 : 4;
     const bool vec = (side & 3u) == 0;
+    const uint32_t valid = nx == 4 ? 0xffffffffu : ((1u << (8 * nx)) - 1u);
+    const uint32_t spawn4 = rep4(spawn), max4 = rep4(stable_max), min4 = rep4(empty_min), empty4 = rep4(empty);
 
-    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) {
-        const uint32_t y = i / side, x = i - y * side;
-        cur[i] = (uint8_t)((world[y * W + (x >> 5)] >> (x & 31)) & 1u);
-        stab[i] = stable[i];
+    for (uint32_t i = threadIdx.x; i < 2 * plane_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem_dyn)[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (side + 2) * (side + 2); i += blockDim.x) {
+        const uint32_t r = i / (side + 2), c = i - r * (side + 2);           // halo coordinates: cell (r - 1, c - 1)
+        const uint32_t y = r == 0 ? side - 1 : (r == side + 1 ? 0 : r - 1);
+        const uint32_t x = c == 0 ? side - 1 : (c == side + 1 ? 0 : c - 1);
+        cur[r * S + 3 + c] = (uint8_t)((world[y * W + (x >> 5)] >> (x & 31)) & 1u);
     }
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) stab[i] = stable[i];
     uint32_t done = last_seq;
     __syncthreads();
 
@@ -180,8 +206,9 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
             }
             const uint32_t action = (uint32_t)c;
             if (action < size) {                                   // toggle_state before the step
-                const uint8_t v = cur[action] ^ 1u;
-                cur[action] = v;
+                const uint32_t y = action / side, x = action - y * side;
+                const uint8_t v = cur[(y + 1) * S + 4 + x] ^ 1u;
+                serve_set_cell(cur, side, S, y, x, v);
                 stab[action] = (masked && !v) ? (int8_t)0 : spawn;
             }
             bc[0] = action;
@@ -197,44 +224,36 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
         uint32_t pop = 0;
         if (lane_ok)
             for (uint32_t y = ty; y < side; y += rows_per_pass) {
-                const uint32_t yu = (y == 0 ? side : y) - 1, yd = (y + 1 == side) ? 0 : y + 1;
-                const uint8_t *ru = cur + yu * side, *rc = cur + y * side, *rd = cur + yd * side;
+                const uint32_t off = (y + 1) * S + 4 + x0;         // 4-byte aligned
+                const uint8_t *rm = cur + off;
+                const uint32_t u = *reinterpret_cast<const uint32_t *>(rm - S);
+                const uint32_t m = *reinterpret_cast<const uint32_t *>(rm);
+                const uint32_t d = *reinterpret_cast<const uint32_t *>(rm + S);
+                const uint32_t lc = (uint32_t)rm[-(int)S - 1] + rm[-1] + rm[S - 1];
+                const uint32_t rc = (uint32_t)rm[4 - (int)S] + rm[4] + rm[S + 4];
+                const uint32_t q = life_next4_bytes(u, m, d, lc, rc) & valid;       // alive next, 0/1 per byte
+                const uint32_t mv = m & valid;
                 const uint32_t base = y * side + x0;
                 uint32_t sv = 0;
                 if (vec) sv = *reinterpret_cast<const uint32_t *>(stab + base);
                 else for (uint32_t k = 0; k < nx; ++k) sv |= (uint32_t)(uint8_t)stab[base + k] << (8 * k);
-                uint32_t col3[6], mid[6];
-#pragma unroll
-                for (uint32_t k = 0; k < 6; ++k) {
-                    if (k >= nx + 2) break;
-                    uint32_t x = x0 + k;                           // column x - 1 on the torus
-                    x = x == 0 ? side - 1 : (x - 1 >= side ? x - 1 - side : x - 1);
-                    mid[k] = rc[x];
-                    col3[k] = ru[x] + mid[k] + rd[x];
+                const uint32_t out = stable_update4_rule(rule, sv, (q & mv) * 255u, (q & ~mv) * 255u, spawn4, max4, min4,
+                                                         empty4) & valid;
+                acc = __dp4a((int)out, 0x01010101, acc);
+                pop += __popc(q);
+                // next world: the cells, and the halo images of the ones on an edge
+                const uint32_t last = (q >> (8 * (nx - 1))) & 1u;
+                for (int ri = 0; ri < 3; ++ri) {
+                    if (ri == 1 && y != 0) continue;
+                    if (ri == 2 && y != side - 1) continue;
+                    uint8_t *row = nxt + (ri == 0 ? y + 1 : (ri == 1 ? side + 1 : 0)) * S;
+                    if (nx == 4) *reinterpret_cast<uint32_t *>(row + 4 + x0) = q;
+                    else for (uint32_t k = 0; k < nx; ++k) row[4 + x0 + k] = (uint8_t)((q >> (8 * k)) & 1u);
+                    if (x0 == 0) row[4 + side] = (uint8_t)(q & 1u);
+                    if (x0 + nx == side) row[3] = (uint8_t)last;
                 }
-                uint32_t out = 0, nbytes = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
-                    if (k >= nx) break;
-                    const uint32_t p = mid[k + 1];
-                    const uint32_t cnt = col3[k] + col3[k + 1] + col3[k + 2] - p;
-                    const uint32_t q = (cnt == 3u) || (cnt == 2u && p);
-                    nbytes |= q << (8 * k);
-                    pop += q;
-                    int8_t s = (int8_t)(sv >> (8 * k));
-                    s = stable_update1_rule(rule, s, p != 0, q != 0, spawn, stable_max, empty, empty_min);
-                    acc += s;
-                    out |= (uint32_t)(uint8_t)s << (8 * k);
-                }
-                if (vec) {
-                    *reinterpret_cast<uint32_t *>(nxt + base) = nbytes;
-                    *reinterpret_cast<uint32_t *>(stab + base) = out;
-                } else {
-                    for (uint32_t k = 0; k < nx; ++k) {
-                        nxt[base + k] = (uint8_t)(nbytes >> (8 * k));
-                        stab[base + k] = (int8_t)(out >> (8 * k));
-                    }
-                }
+                if (vec) *reinterpret_cast<uint32_t *>(stab + base) = out;
+                else for (uint32_t k = 0; k < nx; ++k) stab[base + k] = (int8_t)(out >> (8 * k));
             }
         acc = __reduce_add_sync(0xffffffffu, acc);
         pop = __reduce_add_sync(0xffffffffu, pop);
@@ -261,14 +280,15 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
         if (threadIdx.x == 0)                                      // one 16-byte store: reward, alive and seq arrive together
             asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(result), "r"(red[0]), "r"(red[1]),
                          "r"((int)done), "r"(0) : "memory");
-        uint8_t *t = cur; cur = nxt; nxt = t;
+        uint8_t *tp = cur; cur = nxt; nxt = tp;
     }
 
     // leave: the device planes get the current state back, then the host is told
     for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
         const uint32_t y = i / W, xw = (i - y * W) * 32;
+        const uint8_t *row = cur + (y + 1) * S + 4;
         uint32_t word = 0;
-        for (uint32_t j = 0; j < 32 && xw + j < side; ++j) word |= (uint32_t)cur[y * side + xw + j] << j;
+        for (uint32_t j = 0; j < 32 && xw + j < side; ++j) word |= (uint32_t)row[xw + j] << j;
         world[i] = word;
     }
     for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) stable[i] = stab[i];
@@ -328,6 +348,14 @@ extern "C" int cgl_sim_step_ex(const cgl_sim_step_args_t *a, int32_t action, uin
 
 extern "C" uint32_t cgl_sim_serve_max_side(void) { return SIM1_SERVE_MAX_SIDE; }
 
+// two halo'd byte planes + the stability plane (see sim1_serve_kernel)
+static size_t serve_smem_bytes(uint32_t side)
+{
+    const size_t S = (side + 5u + 3u) & ~3u;
+    const size_t plane = ((side + 2) * S + 15u) & ~(size_t)15u;
+    return 2 * plane + (((size_t)side * side + 15u) & ~(size_t)15u);
+}
+
 // Launch the resident server for one environment (see sim1_serve_kernel).  The world plane that holds the state
 // (world_a if *flip_planes is even, else world_b) and the stability plane are read now and written back when the
 // kernel leaves; flip_planes is not advanced.
@@ -343,13 +371,13 @@ extern "C" int cgl_sim_serve(const cgl_sim_step_args_t *a, const void *cmd_host,
     static PerDeviceOnce once;
     if (once.first())
         CGL_CUDA(cudaFuncSetAttribute(sim1_serve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      3 * SIM1_SERVE_MAX_SIDE * SIM1_SERVE_MAX_SIDE));
-    const uint32_t side = a->side, size = side * side;
+                                      (int)serve_smem_bytes(SIM1_SERVE_MAX_SIDE)));
+    const uint32_t side = a->side;
     const uint32_t W = cgl_words_per_row(side), tpr = (side + 3) / 4;
     uint32_t rows_per_pass = 1024 / tpr;
     if (rows_per_pass > side) rows_per_pass = side;
     const unsigned threads = (tpr * rows_per_pass + 31) / 32 * 32;
-    const size_t smem = 3 * (size_t)((size + 15u) & ~15u);
+    const size_t smem = serve_smem_bytes(side);
     const bool flip = (a->flip_planes != nullptr) && (*a->flip_planes & 1u);
     sim1_serve_kernel<<<1, threads, smem, as_stream(stream)>>>(
         flip ? a->world_b_dev : a->world_a_dev, a->stable_dev, side, W, (int8_t)a->spawn, (int8_t)a->stable_max,

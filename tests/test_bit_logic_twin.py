@@ -181,3 +181,21 @@ def test_bit_sliced_decay_rule_equals_scalar_rule(twin, spawn, smax, emin):
     cells[768:790] = np.int8(emin)                      # whole groups on the floor / at the ceiling
     cells[790:812] = np.int8(smax)
     assert twin.twin_sliced_decay_mismatches(P(cells), P(tr), groups, spawn, smax, emin) == 0
+
+
+def test_packed_byte_generation_equals_scalar_rule(twin):
+    """life_next4_bytes (the single-env server's generation, 4 cells per word): EVERY 3 x 6 neighbourhood of a
+    4-cell group against the scalar B3/S23 rule."""
+    n = 1 << 18
+    bits = ((np.arange(n, dtype=np.uint32)[:, None] >> np.arange(18, dtype=np.uint32)[None, :]) & 1).reshape(n, 3, 6)
+    rows = bits.astype(np.uint32)                                  # rows[:, r, c]: column c = x0 - 1 + c
+    words = [np.ascontiguousarray(sum(rows[:, r, 1 + k] << (8 * k) for k in range(4)).astype(np.uint32)) for r in range(3)]
+    lc = np.ascontiguousarray(rows[:, :, 0].sum(axis=1).astype(np.uint32))
+    rc = np.ascontiguousarray(rows[:, :, 5].sum(axis=1).astype(np.uint32))
+    out = np.zeros(n, np.uint32)
+    twin.twin_life_next4_bytes.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint64]
+    twin.twin_life_next4_bytes(P(words[0]), P(words[1]), P(words[2]), P(lc), P(rc), P(out), n)
+    for k in range(4):
+        cnt = rows[:, :, k:k + 3].sum(axis=(1, 2)) - rows[:, 1, 1 + k]
+        want = ((cnt == 3) | ((cnt == 2) & (rows[:, 1, 1 + k] == 1))).astype(np.uint32)
+        assert np.array_equal((out >> (8 * k)) & 0xff, want), k

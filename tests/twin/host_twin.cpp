@@ -359,4 +359,11 @@ int twin_env_step_fused_rule(const uint32_t *world_in, uint32_t *world_out, int8
     return err;
 }
 
+// the single-env server's packed-byte generation (cgl_bits.cuh life_next4_bytes), vectorised over n cases
+void twin_life_next4_bytes(const uint32_t *u, const uint32_t *m, const uint32_t *d, const uint32_t *lc,
+                           const uint32_t *rc, uint32_t *out, uint64_t n)
+{
+    for (uint64_t i = 0; i < n; ++i) out[i] = cgl::life_next4_bytes(u[i], m[i], d[i], lc[i], rc[i]);
+}
+
 }  // extern "C"
