@@ -71,6 +71,91 @@ __device__ __forceinline__ void emit_row(const RowSums &up, const RowSums &mid, 
     if (COUNT && r < (int)L.rows) pop += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
 }
 
+// The general strip walk: any row index (rows outside [0, rows) wrap or are dead), stores predicated per row.
+template <bool COUNT, int PF>
+__device__ __forceinline__ void walk_general(const Lane &L, uint32_t *__restrict__ gout, const int r0, const int rpt,
+                                             unsigned &pop)
+{
+    RowSums A, B, C;
+    row_sums(A, load_row_raw(L, r0 - 1), L);
+    row_sums(B, load_row_raw(L, r0), L);
+
+    RowRaw nxt[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r0 + u + 1);
+
+    for (int i = 0; i < rpt; i += PF) {                        // uniform trip count
+        const int r = r0 + i;
+        RowRaw cur[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        if (i + PF < rpt) {                                    // uniform: prefetch the next trip's rows
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r + PF + u + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < PF; u += 3) {
+            row_sums(C, cur[u], L);     emit_row<COUNT>(A, B, C, gout, L, r + u, pop);
+            row_sums(A, cur[u + 1], L); emit_row<COUNT>(B, C, A, gout, L, r + u + 1, pop);
+            row_sums(B, cur[u + 2], L); emit_row<COUNT>(C, A, B, gout, L, r + u + 2, pop);
+        }
+    }
+}
+
+// The interior strip walk: every row touched is a real row of the grid, so a row is `pointer += W`.
+template <bool COUNT>
+__device__ __forceinline__ void emit_row_at(const RowSums &up, const RowSums &mid, const RowSums &dn, uint32_t *po,
+                                            const Lane &L, unsigned &pop)
+{
+    uint4 o;
+    o.x = life_rule(up.h[0], mid.h[0], dn.h[0], mid.c.x);
+    o.y = life_rule(up.h[1], mid.h[1], dn.h[1], mid.c.y);
+    o.z = life_rule(up.h[2], mid.h[2], dn.h[2], mid.c.z);
+    o.w = life_rule(up.h[3], mid.h[3], dn.h[3], mid.c.w);
+    if (L.store) *reinterpret_cast<uint4 *>(po) = o;
+    if (COUNT) pop += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
+}
+
+template <bool COUNT, int PF>
+__device__ __forceinline__ void walk_interior(const Lane &L, uint32_t *__restrict__ gout, const int r0, const int rpt,
+                                              unsigned &pop)
+{
+    const uint32_t W = L.W;
+    const uint32_t *pm = L.gin + (uint64_t)(uint32_t)(r0 - 1) * W + 4 * L.c4;      // this lane's uint4 of row r0 - 1
+    const int hoff = (int)L.hidx - 4 * (int)L.c4;                                  // halo word relative to it
+    uint32_t *po = gout + (uint64_t)(uint32_t)r0 * W + 4 * L.c4;
+    auto load = [&](const uint32_t *p) {
+        RowRaw o;
+        o.v = make_uint4(0, 0, 0, 0);
+        o.halo = 0;
+        if (L.valid) o.v = __ldg(reinterpret_cast<const uint4 *>(p));
+        if (L.edge) o.halo = __ldg(p + hoff);
+        return o;
+    };
+    RowSums A, B, C;
+    row_sums(A, load(pm), L); pm += W;
+    row_sums(B, load(pm), L); pm += W;
+    RowRaw nxt[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { nxt[u] = load(pm); pm += W; }
+
+    for (int i = 0; i < rpt; i += PF) {                        // uniform trip count
+        RowRaw cur[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        if (i + PF < rpt) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) { nxt[u] = load(pm); pm += W; }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; u += 3) {
+            row_sums(C, cur[u], L);     emit_row_at<COUNT>(A, B, C, po, L, pop); po += W;
+            row_sums(A, cur[u + 1], L); emit_row_at<COUNT>(B, C, A, po, L, pop); po += W;
+            row_sums(B, cur[u + 2], L); emit_row_at<COUNT>(C, A, B, po, L, pop); po += W;
+        }
+    }
+}
+
 constexpr int LIFE_ROWS_THREADS = 128;   // 4 warps = 4 horizontally adjacent column groups
 
 // rpt must be a multiple of PF (PF a multiple of 3); strips may run past `rows` (loads wrap / are
@@ -78,12 +163,16 @@ constexpr int LIFE_ROWS_THREADS = 128;   // 4 warps = 4 horizontally adjacent co
 // sums rotates through three register sets A, B, C without moves.  The rows of trip i+1 are loaded
 // (software pipelining) before trip i is computed, which keeps PF 16-byte loads per thread in
 // flight whatever the instruction scheduler does inside a trip.
-template <bool COUNT, int PF>
-__global__ void __launch_bounds__(LIFE_ROWS_THREADS)
+template <bool COUNT, int PF, int MINB>
+__global__ void __launch_bounds__(LIFE_ROWS_THREADS, MINB)
 life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_envs,
                  uint32_t rows, uint32_t W, uint32_t rpt, int wrap_rows, uint32_t n_cgroups,
                  uint32_t n_rblocks, uint32_t *__restrict__ alive_out)
 {
+    // Programmatic dependent launch: the next generation's CTAs may be placed while this grid's last wave drains;
+    // they (like this CTA) wait for the whole previous grid before touching memory -- consecutive generations
+    // ping-pong the two buffers, so a generation may neither read its input nor overwrite its output earlier.
+    cudaTriggerProgrammaticLaunchCompletion();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (LIFE_ROWS_THREADS / 32) + (threadIdx.x >> 5);
     const uint32_t cg = warp % n_cgroups;
@@ -108,31 +197,22 @@ life_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
     uint32_t *gout = out + (uint64_t)e * rows * W;
 
     const int r0 = (int)(rb * rpt);
-    RowSums A, B, C;
-    row_sums(A, load_row_raw(L, r0 - 1), L);
-    row_sums(B, load_row_raw(L, r0), L);
     unsigned pop = 0;
-
-    RowRaw nxt[PF];
+    cudaGridDependencySynchronize();
+    // Strips whose rows r0 - 1 .. r0 + rpt all lie inside the grid (all but the first and last of an env) take the
+    // lean walk: running pointers, no wrap / dead-row selects, unpredicated row tests.
+    // (decided per CTA from blockIdx and kernel parameters only, so that the compiler can prove it uniform)
+    bool cta_interior = true;
 #pragma unroll
-    for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r0 + u + 1);
-
-    for (int i = 0; i < (int)rpt; i += PF) {                   // uniform trip count
-        const int r = r0 + i;
-        RowRaw cur[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
-        if (i + PF < (int)rpt) {                               // uniform: prefetch the next trip's rows
-#pragma unroll
-            for (int u = 0; u < PF; ++u) nxt[u] = load_row_raw(L, r + PF + u + 1);
-        }
-#pragma unroll
-        for (int u = 0; u < PF; u += 3) {
-            row_sums(C, cur[u], L);     emit_row<COUNT>(A, B, C, gout, L, r + u, pop);
-            row_sums(A, cur[u + 1], L); emit_row<COUNT>(B, C, A, gout, L, r + u + 1, pop);
-            row_sums(B, cur[u + 2], L); emit_row<COUNT>(C, A, B, gout, L, r + u + 2, pop);
-        }
+    for (uint32_t k = 0; k < LIFE_ROWS_THREADS / 32; ++k) {
+        const uint32_t tk = (blockIdx.x * (LIFE_ROWS_THREADS / 32) + k) / n_cgroups;
+        const uint32_t rk = (tk % n_rblocks) * rpt;
+        cta_interior = cta_interior && rk >= 1 && rk + rpt + 1 <= rows && tk / n_rblocks < n_envs;
     }
+    if (cta_interior)
+        walk_interior<COUNT, PF>(L, gout, r0, (int)rpt, pop);
+    else
+        walk_general<COUNT, PF>(L, gout, r0, (int)rpt, pop);
     if (COUNT) {
         if (!L.store) pop = 0;
         pop = __reduce_add_sync(0xffffffffu, pop);
@@ -183,17 +263,40 @@ extern "C" int cgl_life_step(const uint32_t *in, uint32_t *out, uint64_t n_envs,
         const char *v = getenv("CGL_LIFE_PF");
         pf = (v && atoi(v) == 6) ? 6 : 3;
     }
+    static int minb = 0;                         // tuning knob: resident CTAs per SM the register allocation aims for (5 or 6)
+    if (minb == 0) {
+        const char *v = getenv("CGL_LIFE_MINB");
+        minb = (v && atoi(v) == 5) ? 5 : 6;
+    }
+    static int pdl = -1;                         // CGL_LIFE_PDL=0: plain stream order (tuning / debugging)
+    if (pdl < 0) {
+        const char *v = getenv("CGL_LIFE_PDL");
+        pdl = (v && v[0] == '0') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(LIFE_ROWS_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const uint32_t n32 = (uint32_t)n_envs;
+#define CGL_LIFE_ROWS(COUNT, PF, MINB, AL)                                                                        \
+    CGL_CUDA(cudaLaunchKernelEx(&cfg, life_rows_kernel<COUNT, PF, MINB>, in, out, n32, rows, W, rpt, wrap_rows,    \
+                                n_cgroups, n_rblocks, (uint32_t *)(AL)))
     if (alive_out != nullptr) {
         CGL_CUDA(cudaMemsetAsync(alive_out, 0, n_envs * sizeof(uint32_t), st));
-        life_rows_kernel<true, 3><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
-            in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, alive_out);
+        CGL_LIFE_ROWS(true, 3, 5, alive_out);
     } else if (pf == 6) {
-        life_rows_kernel<false, 6><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
-            in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, nullptr);
+        CGL_LIFE_ROWS(false, 6, 4, nullptr);
+    } else if (minb == 5) {
+        CGL_LIFE_ROWS(false, 3, 5, nullptr);
     } else {
-        life_rows_kernel<false, 3><<<(unsigned)blocks, LIFE_ROWS_THREADS, 0, st>>>(
-            in, out, (uint32_t)n_envs, rows, W, rpt, wrap_rows, n_cgroups, n_rblocks, nullptr);
+        CGL_LIFE_ROWS(false, 3, 6, nullptr);
     }
+#undef CGL_LIFE_ROWS
     CGL_LAUNCH_CHECK();
     return 0;
 }
