@@ -14,8 +14,9 @@ data-path collective).  A "step" is one launch of the fused kernel over all envs
 
 Prints ONE JSON line (rank 0).
   value      G cell-updates/s over all ranks, state resident in HBM.  The K steps of a timed region are issued by ONE
-             C-ABI call (cgl_env_step_seq: K launches back to back); the region is bracketed by barrier +
-             synchronize on both sides and timed with CUDA events; it is repeated --repeats times and the MEDIAN
+             C-ABI call (cgl_env_step_seq_timed: K launches back to back, the two CUDA events recorded on the stream
+             right before the first and after the last launch); the region is bracketed by barrier + synchronize
+             on both sides; it is repeated --repeats times and the MEDIAN
              region (max over ranks each) is reported, all of them listed in `regions_ms`.
   e2e        the same metric through the host-driven rollout (cgl_b200.rollout.HostRollout -> cgl_rollout_run):
              every step every env receives its action from pinned host memory (H2D copy inside the timed region)
@@ -270,23 +271,29 @@ def setup_dist():
     return c
 
 
-def timed_region(c, issue):
-    """ONE timed region: barrier + synchronize, CUDA events around issue(), synchronize + barrier.  Seconds."""
+def timed_region(c, issue, events=None):
+    """ONE timed region: barrier + synchronize, CUDA events around issue(), synchronize + barrier.  Seconds.
+    events = (e0, e1): issue() records them itself on the launching stream, right before its first and right after
+    its last launch (StepSequence.prepare(K, events=...) -> cgl_env_step_seq_timed)."""
     torch = c.torch
     c.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    issue()
-    e1.record()
+    if events is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        issue()
+        e1.record()
+    else:
+        e0, e1 = events
+        issue()
     torch.cuda.synchronize()
     c.barrier()
     return e0.elapsed_time(e1) / 1e3
 
 
-def repeat_regions(c, issue, repeats):
+def repeat_regions(c, issue, repeats, events=None):
     """`repeats` timed regions; every region's time is the max over ranks; returns (median, all)."""
-    ts = [c.max_over_ranks(timed_region(c, issue)) for _ in range(repeats)]
+    ts = [c.max_over_ranks(timed_region(c, issue, events)) for _ in range(repeats)]
     return statistics.median(ts), ts
 
 
@@ -348,9 +355,10 @@ def run_c2_line(c, args):
 
     # ---- headline: K steps per region, issued by one C-ABI call (K launches) --------------------------------
     sampler = ClockSampler(c.local).start() if rank == 0 else None
-    issue = seq.prepare(K)
+    events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    issue = seq.prepare(K, events=events)
     issue(); issue()                                        # (both plane orientations of an odd K are cached now)
-    dt_eager, regions_eager = repeat_regions(c, issue, args.repeats)
+    dt_eager, regions_eager = repeat_regions(c, issue, args.repeats, events)
 
     # L2-resident variant (one replica, 80 MiB working set inside the 126 MB L2) -- reported, not the headline
     seq1 = StepSequence(sims[:1], actions)

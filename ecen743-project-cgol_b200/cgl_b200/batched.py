@@ -535,11 +535,15 @@ class StepSequence:
         """Enqueue n_steps steps (step i: sims[i % R], actions[i % A]) on the current stream.  Returns at once."""
         self.prepare(n_steps)()
 
-    def prepare(self, n_steps: int):
-        """Everything run() can do ahead of time, done now; returns a function that issues the n_steps launches: a
-        cache lookup for the descriptor cycle of the current plane orientation, ONE C-ABI call, then the plane
-        bookkeeping.  A benchmark calls prepare() outside its timed region so that the region starts with the first
-        launch, not with Python.  The function may be called any number of times (planes may flip in between)."""
+    def prepare(self, n_steps: int, events=None):
+        """Everything run() can do ahead of time, done now; returns a function that issues the n_steps launches.
+        The function's FIRST action is the one C-ABI call (descriptor cycle, token state and stream were resolved
+        beforehand -- by prepare() for the first call, by the previous call for the next one); the plane
+        bookkeeping and the look-up for the following call come after it, while the GPU is already busy.  A benchmark
+        calls prepare() outside its timed region so that the region starts with the first launch, not with Python.
+        events = (start, stop): two torch.cuda.Event(enable_timing=True) that the library records on the stream
+        right before the first and after the last launch (cgl_env_step_seq_timed).  The function may be called any
+        number of times (planes may flip in between, other calls may step the sims in between)."""
         sims = self.sims
         s0 = sims[0]
         for s in sims:
@@ -548,20 +552,40 @@ class StepSequence:
         if torch.cuda.current_device() != s0.device.index:
             torch.cuda.set_device(s0.device)
         stream = s0._stream()
-        fn, alarm = self._lib.cgl_env_step_seq, s0._alarm
-        self._descs()                                       # warm the cache for the current orientation
+        alarm = s0._alarm
+        if events is not None:
+            for e in events:
+                e.record()                                  # (creates the underlying cudaEvent_t)
+            ev0, ev1 = (ctypes.c_void_p(e.cuda_event) for e in events)
+            seq_fn = self._lib.cgl_env_step_seq_timed
+            fn = lambda descs, n: seq_fn(descs, n, n_steps, 0, stream, ev0, ev1)      # noqa: E731
+        else:
+            seq_fn = self._lib.cgl_env_step_seq
+            fn = lambda descs, n: seq_fn(descs, n, n_steps, 0, stream)               # noqa: E731
+        state = {}
 
-        def issue():
-            if alarm[1]:
-                native.check_alarm()
+        def resolve():
             descs, n, modes = self._descs()
             for s, mode in zip(sims, modes):
                 if mode and (mode == native.CHAIN_IDS or s._tok is None):
                     s._sync_tokens(mode, s._wa.data_ptr())
-            rc = fn(descs, n, n_steps, 0, stream)
+            state["key"] = tuple(s._wa.data_ptr() for s in sims) + tuple(s.count for s in sims)
+            state["args"] = (descs, n, modes)
+
+        resolve()
+
+        def issue():
+            # valid as long as nobody stepped the sims since resolve() (one tuple compare); otherwise resolve again
+            if state["key"] != tuple(s._wa.data_ptr() for s in sims) + tuple(s.count for s in sims):
+                resolve()
+            descs, n, modes = state["args"]
+            rc = fn(descs, n)
             if rc:
                 native.check(rc, "cgl_env_step_seq")
             self._after(n_steps, modes)
+            if alarm[1]:
+                native.check_alarm()
+            resolve()
         return issue
 
     def _after(self, n_steps, modes):

@@ -89,6 +89,7 @@ class EnvStepArgs(ctypes.Structure):
 CHAIN_NONE, CHAIN_IDS, CHAIN_SEQ = 0, 1, 2
 SIGNATURES["cgl_env_step_ex"] = (_i, [ctypes.POINTER(EnvStepArgs), _vp])
 SIGNATURES["cgl_env_step_seq"] = (_i, [ctypes.POINTER(EnvStepArgs), _u32, _u64, _u64, _vp])
+SIGNATURES["cgl_env_step_seq_timed"] = (_i, [ctypes.POINTER(EnvStepArgs), _u32, _u64, _u64, _vp, _vp, _vp])
 
 class SimStepArgs(ctypes.Structure):
     """cgl_sim_step_args_t (include/cgl_b200.h)."""

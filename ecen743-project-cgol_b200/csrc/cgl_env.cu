@@ -859,6 +859,21 @@ extern "C" int cgl_env_step_seq(const cgl_env_step_args_t *steps, uint32_t n_des
     return 0;
 }
 
+// The same with the caller's two CUDA events recorded on `stream` right before the first and right after the last
+// launch: a timed region then starts with the first launch instead of with the binding's call overhead.
+extern "C" int cgl_env_step_seq_timed(const cgl_env_step_args_t *steps, uint32_t n_descs, uint64_t n_steps, uint64_t first,
+                                      cgl_stream_t stream, void *start_event, void *stop_event)
+{
+    CGL_REQUIRE(steps && n_descs, CGL_E_BADARG, "cgl_env_step_seq_timed: bad argument");
+    if (start_event) CGL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(start_event), as_stream(stream)));
+    for (uint64_t i = 0; i < n_steps; ++i) {
+        const int rc = cgl_env_step_ex(&steps[(first + i) % n_descs], stream);
+        if (rc) return rc;
+    }
+    if (stop_event) CGL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(stop_event), as_stream(stream)));
+    return 0;
+}
+
 // Out-of-place form: the new stability plane goes to `stable_out` (see include/cgl_b200.h).
 extern "C" int cgl_env_step_io(uint32_t *win, uint32_t *wout, const int8_t *stable_in, int8_t *stable_out,
                                uint64_t n_envs, uint32_t side, const int32_t *actions, int spawn, int stable_max,

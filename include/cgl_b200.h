@@ -161,6 +161,11 @@ int cgl_env_step_ex(const cgl_env_step_args_t *args, cgl_stream_t stream);
  * asynchronously.  The descriptors must stay valid only for the duration of the call. */
 int cgl_env_step_seq(const cgl_env_step_args_t *steps, uint32_t n_descs, uint64_t n_steps, uint64_t first,
                      cgl_stream_t stream);
+/* cgl_env_step_seq with two CUDA events (cudaEvent_t, may be NULL) recorded on `stream` immediately before the first
+ * and after the last launch -- for timing a region of K steps on the device without the binding's call overhead
+ * between the start event and the first launch (bench.py). */
+int cgl_env_step_seq_timed(const cgl_env_step_args_t *steps, uint32_t n_descs, uint64_t n_steps, uint64_t first,
+                           cgl_stream_t stream, void *start_event, void *stop_event);
 
 /* Out-of-place env step: as cgl_env_step / cgl_env_step_chained (token_dev == NULL: plain stream order;
  * otherwise the chained form), but the stability plane is READ from stable_in_dev and the new plane is
