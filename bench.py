@@ -726,8 +726,15 @@ def single_gpu_extras(c, peak, lib):
         dt = time_steps(c, lambda _i: env.run(k), 3) / 3
         runk[f"k{k}"] = {"gcups": 4096 * 128 * 128 * k / dt / 1e9, "us_per_step": dt / k * 1e6,
                          "env_steps_per_s": 4096 * k / dt}
-    out["f3_run_in_smem_4096x128"] = runk
     del env
+    for rule in ("decay", "sat"):                            # the fork's rules on chip (bit planes), 64 steps per launch
+        env = BatchedSim(4096, 128, seed=0, spawnStabilityFactor=SPAWN, stableStabilityFactor=STABLE, rng="device",
+                         dead_rule=rule, empty=-1, empty_min=-6, masked_toggle=True)
+        env.run(64)
+        dt = time_steps(c, lambda _i: env.run(64), 3) / 3
+        runk[f"k64_{rule}"] = {"gcups": 4096 * 128 * 128 * 64 / dt / 1e9, "us_per_step": dt / 64 * 1e6}
+        del env
+    out["f3_run_in_smem_4096x128"] = runk
     # f2: the CGL_action+ fork's rule (dead cells decay to a floor, masked toggle) in the same fused kernel
     g = torch.Generator(device=dev)
     g.manual_seed(11)

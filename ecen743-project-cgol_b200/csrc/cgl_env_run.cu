@@ -259,15 +259,17 @@ struct SlicedCfg {
     static constexpr int SMEM = EPC * (4 * WPE * 4) + EPC * 8;
 };
 
-// DECAY = false: the base env (dead cells are 0; "don't care" planes).  DECAY = true: the CGL_action+ fork's
-// CUDA-kernel rule (dead cells fall by one per step to EMPTY_MIN), all cells carried spawn-relative.
-template <int S, bool DECAY>
+// RULE = CGL_DEAD_ZERO: the base env (dead cells are 0; "don't care" planes, spawn-relative).  CGL_DEAD_DECAY: the
+// CGL_action+ fork's CUDA-kernel rule (dead cells fall by one per step to EMPTY_MIN), all cells carried
+// spawn-relative.  CGL_DEAD_SAT: the fork's CPU rule (dead cells become min(s + EMPTY, EMPTY_MIN)) on absolute planes.
+template <int S, int RULE>
 __global__ void __launch_bounds__(SlicedCfg<S>::THREADS)
 env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *stable, uint32_t n_envs,
                       uint32_t max_steps, int stop_when_fixed, int spawn, int stable_max, int empty_min,
                       int32_t *__restrict__ steps_out, int32_t *__restrict__ reward_out,
-                      uint32_t *__restrict__ alive_out)
+                      uint32_t *__restrict__ alive_out, int empty)
 {
+    constexpr bool DECAY = RULE == CGL_DEAD_DECAY, SAT = RULE == CGL_DEAD_SAT;
     using C = SlicedCfg<S>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int g = threadIdx.x / C::TPE;
@@ -292,7 +294,7 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
                 const uint4 b = sp[((t * C::RPB + j) * S + w * 32) / 16 + 1];
                 const uint32_t by[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 bytes_to_planes32(by, pl[j][w]);
-                add_const_sliced(pl[j][w], -spawn);             // spawn-relative planes (cgl_bits.cuh)
+                if constexpr (!SAT) add_const_sliced(pl[j][w], -spawn);     // spawn-relative planes (cgl_bits.cuh)
             }
         }
     }
@@ -351,7 +353,8 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
                     const uint32_t c = cw[j][w];
                     const uint32_t n = life_rule(up, hs[j][w], dn, c);
                     changed |= n ^ c;
-                    if constexpr (DECAY) stable_update_sliced_decay(pl[j][w], n & c, n & ~c, max_rel, min_rel);
+                    if constexpr (SAT) stable_update_sliced_sat(pl[j][w], n & c, n & ~c, spawn, stable_max, empty, empty_min);
+                    else if constexpr (DECAY) stable_update_sliced_decay(pl[j][w], n & c, n & ~c, max_rel, min_rel);
                     else stable_update_sliced_rel(pl[j][w], n & c, max_rel);
                     cw[j][w] = n;
                 }
@@ -372,8 +375,8 @@ env_run_sliced_kernel(const uint32_t *world_in, uint32_t *world_out, int8_t *sta
 #pragma unroll
             for (int w = 0; w < C::W; ++w) {
                 pop += __popc(cw[j][w]);
-                add_const_sliced(pl[j][w], spawn);              // back to absolute values; dead cells are 0
-                if constexpr (!DECAY) {
+                if constexpr (!SAT) add_const_sliced(pl[j][w], spawn);      // back to absolute values; dead cells are 0
+                if constexpr (!DECAY && !SAT) {
 #pragma unroll
                     for (int b = 0; b < 8; ++b) pl[j][w][b] &= cw[j][w];
                 }
@@ -501,14 +504,16 @@ static int launch_env_run(const uint32_t *win, uint32_t *wout, int8_t *stable, u
     if (once.first())
         CGL_CUDA(cudaFuncSetAttribute(env_run_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     const unsigned grid = (unsigned)((n_envs + C::EPC - 1) / C::EPC);
-    if (rule != CGL_DEAD_SAT && run_use_sliced(max_steps)) {       // (the saturating rule stays on the byte kernel)
+    if (run_use_sliced(max_steps)) {
         using D = SlicedCfg<S>;
-        if (rule == CGL_DEAD_DECAY)
-            env_run_sliced_kernel<S, true><<<grid, D::THREADS, D::SMEM, st>>>(
-                win, wout, stable, (uint32_t)n_envs, max_steps, stop, spawn, stable_max, empty_min, steps, reward, alive);
-        else
-            env_run_sliced_kernel<S, false><<<grid, D::THREADS, D::SMEM, st>>>(
-                win, wout, stable, (uint32_t)n_envs, max_steps, stop, spawn, stable_max, empty_min, steps, reward, alive);
+#define CGL_RUN_SLICED(RULE)                                                                                          \
+    env_run_sliced_kernel<S, RULE><<<grid, D::THREADS, D::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, \
+                                                                       stop, spawn, stable_max, empty_min, steps,      \
+                                                                       reward, alive, empty)
+        if (rule == CGL_DEAD_DECAY) CGL_RUN_SLICED(CGL_DEAD_DECAY);
+        else if (rule == CGL_DEAD_SAT) CGL_RUN_SLICED(CGL_DEAD_SAT);
+        else CGL_RUN_SLICED(CGL_DEAD_ZERO);
+#undef CGL_RUN_SLICED
     } else {
         env_run_kernel<S><<<grid, C::THREADS, C::SMEM, st>>>(win, wout, stable, (uint32_t)n_envs, max_steps, stop,
                                                             rep4(spawn), rep4(stable_max), steps, reward, alive, rule,

@@ -199,3 +199,25 @@ def test_packed_byte_generation_equals_scalar_rule(twin):
         cnt = rows[:, :, k:k + 3].sum(axis=(1, 2)) - rows[:, 1, 1 + k]
         want = ((cnt == 3) | ((cnt == 2) & (rows[:, 1, 1 + k] == 1))).astype(np.uint32)
         assert np.array_equal((out >> (8 * k)) & 0xff, want), k
+
+
+@pytest.mark.parametrize("spawn,smax,empty,emin", [(-2, 2, -1, -6), (-128, 127, -128, -128), (5, 127, 3, -3), (-2, 3, -1, 127),
+                                                   (0, 0, 0, 0), (7, -3, 100, 100), (-2, 2, 127, 5), (-100, 20, -50, -120)])
+def test_bit_sliced_saturating_rule_equals_scalar_rule(twin, spawn, smax, empty, emin):
+    """stable_update_sliced_sat (the fork's CPU rule on absolute bit planes): every int8 value under every transition,
+    including sums that wrap before the signed minimum is taken."""
+    twin.twin_sliced_sat_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    twin.twin_sliced_sat_mismatches.restype = ctypes.c_uint64
+    rs = np.random.RandomState(abs(spawn) + abs(emin) + abs(empty))
+    groups = 256 * 3 + 400
+    cells = rs.randint(-128, 128, size=(groups, 32)).astype(np.int8)
+    tr = rs.randint(0, 3, size=(groups, 32)).astype(np.uint8)
+    for v in range(256):
+        for t in range(3):
+            pos = rs.randint(32)
+            cells[v * 3 + t, pos] = np.int8(v - 128)
+            tr[v * 3 + t, pos] = t
+    cells[768:790] = np.int8(emin)
+    cells[790:812] = np.int8(smax)
+    assert twin.twin_sliced_sat_mismatches(P(cells), P(tr), groups, spawn, smax, empty, emin) == 0

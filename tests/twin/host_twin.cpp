@@ -236,6 +236,31 @@ uint64_t twin_sliced_decay_mismatches(const int8_t *cells, const uint8_t *tr, ui
     return bad;
 }
 
+// The fork's saturating rule on absolute bit planes against the scalar rule (tr: 0 survive, 1 born, 2 dead).
+uint64_t twin_sliced_sat_mismatches(const int8_t *cells, const uint8_t *tr, uint64_t n_groups, int spawn, int stable_max,
+                                    int empty, int empty_min)
+{
+    uint64_t bad = 0;
+    for (uint64_t g = 0; g < n_groups; ++g) {
+        uint32_t w[8], p[8], back[8], surv = 0, born = 0;
+        memcpy(w, cells + 32 * g, 32);
+        bytes_to_planes32(w, p);
+        for (int j = 0; j < 32; ++j) {
+            if (tr[32 * g + j] == 0) surv |= 1u << j;
+            if (tr[32 * g + j] == 1) born |= 1u << j;
+        }
+        stable_update_sliced_sat(p, surv, born, spawn, stable_max, empty, empty_min);
+        planes_to_bytes32(p, back);
+        for (int j = 0; j < 32; ++j) {
+            const int8_t want = stable_update1_rule(CGL_DEAD_SAT, cells[32 * g + j], tr[32 * g + j] == 0,
+                                                    tr[32 * g + j] != 2, (int8_t)spawn, (int8_t)stable_max, (int8_t)empty,
+                                                    (int8_t)empty_min);
+            bad += ((const int8_t *)back)[j] != want;
+        }
+    }
+    return bad;
+}
+
 // mirrors env_run_sliced_kernel<S, DECAY> (csrc/cgl_env_run.cu) for ONE env, side % 32 == 0: rows of the world
 // and spawn-relative bit planes per row owner, horizontal sums (s0, s1) published once per row and step, the
 // vote on the PREVIOUS step's change taken at the same point as the kernel's barrier.  Returns the steps executed.
