@@ -87,6 +87,32 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 
 struct RuleArgs { int rule, empty, empty_min, masked; };
 
+// nibble -> byte mask (bit i -> byte i = 0xFF), the 16 values of nibble_to_bytemask()
+__constant__ uint32_t c_bytemask16[16] = {
+    0x00000000u, 0x000000ffu, 0x0000ff00u, 0x0000ffffu, 0x00ff0000u, 0x00ff00ffu, 0x00ffff00u, 0x00ffffffu,
+    0xff000000u, 0xff0000ffu, 0xff00ff00u, 0xff00ffffu, 0xffff0000u, 0xffff00ffu, 0xffffff00u, 0xffffffffu};
+
+// Fill the lane-private mask tables: word (nib*64 + which*32 + lane) = mask(nib) [& SPAWN if which].  Every CTA does
+// this once, so it is kept short: with a thread count that is a multiple of 64 a thread's `which` and its nibble
+// sequence are fixed, and an entry is one constant-bank load (warp-uniform index), one AND and one store.
+template <int THREADS>
+__device__ __forceinline__ void fill_mask_tables(uint32_t *tables, uint32_t spawn4)
+{
+    if constexpr (THREADS % 64 == 0) {
+        const uint32_t andm = (threadIdx.x & 32u) ? spawn4 : 0xffffffffu;
+        const uint32_t nb0 = threadIdx.x >> 6;
+#pragma unroll
+        for (int k = 0; k < (1024 + THREADS - 1) / THREADS; ++k)
+            if (k * THREADS + THREADS <= 1024 || threadIdx.x + k * THREADS < 1024)
+                tables[threadIdx.x + k * THREADS] = c_bytemask16[nb0 + k * (THREADS / 64)] & andm;
+    } else {
+        for (int i = threadIdx.x; i < 1024; i += THREADS) {
+            const uint32_t m = c_bytemask16[(uint32_t)i >> 6];
+            tables[i] = (i & 32) ? (m & spawn4) : m;
+        }
+    }
+}
+
 // IO = false: the stability plane is updated in place.  IO = true: it is read from `stable` and the
 // new values go to `stable_out` (another buffer of the same shape) -- the replay ring of the batched
 // DQN loop hands the env its next observation slot, so "adding to the replay buffer" costs no copy.
@@ -163,10 +189,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         if (C::EPC == 1 && active && !seq_tokens)
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v_seen) : "l"(epoch + e) : "memory");
         if (t == 0 && active) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(epoch + e) : "memory");
-        for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
-            const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
-            tables[i] = (i & 32) ? (m & spawn4) : m;
-        }
+        fill_mask_tables<C::THREADS>(tables, spawn4);
         const bool seen = seq_tokens || (C::EPC == 1 && v_seen == want);     // seen: already triggered
         if (seen && !seq_tokens) cudaTriggerProgrammaticLaunchCompletion();
         if (t == 0) {
@@ -196,12 +219,7 @@ env_step_fused_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         for (int u = 0; u < C::UNR; ++u) sreg[u] = (sp + t)[u * C::TPE];
     }
 
-    if (epoch == nullptr) {
-        for (int i = threadIdx.x; i < 1024; i += C::THREADS) {
-            const uint32_t m = nibble_to_bytemask((uint32_t)i >> 6);
-            tables[i] = (i & 32) ? (m & spawn4) : m;
-        }
-    }
+    if (epoch == nullptr) fill_mask_tables<C::THREADS>(tables, spawn4);
     if (t == 0) { red[0] = 0; red[1] = 0; }
 
     // ---- action decode (toggle_state before step, CGL/main.py:66-67) ----------------------
