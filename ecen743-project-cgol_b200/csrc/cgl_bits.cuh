@@ -150,12 +150,14 @@ CGL_HD uint32_t dead_value4(int rule, uint32_t s, uint32_t min4, uint32_t empty4
     return 0u;
 }
 
-// The decay rule for 4 cells as ONE equality test and ONE bytewise addition.  A cell is a survivor, dead or born;
-// survivors compare against MAX and add 1, dead cells compare against MIN and add -1, born cells are overwritten
-// with SPAWN at the end (whatever was computed for them).  So the constant a byte is compared with is SELECTED per
-// byte (one LOP3), the "byte != constant" test leaves its answer in bit 7, bit 7 -> 0x00 / 0xFF runs on the FMA pipe
-// (IMAD.HI / IMAD, which the integer-pipe-bound kernel has to spare) and one more LOP3 turns 0xFF into the delta
-// 0x01 for survivors.  11 integer-pipe operations per 4 cells (the two-test form it replaces took 16).
+// The decay rule for 4 cells as ONE equality test and ONE bytewise INCREMENT.  A cell is a survivor, dead or born;
+// survivors compare against MAX and add 1, dead cells compare against MIN and subtract 1, born cells are overwritten
+// with SPAWN at the end (whatever was computed for them).  The constant a byte is compared with is SELECTED per byte
+// (one LOP3); "byte != constant" leaves a 0/1 per byte (bit 7 -> bit 0 on the FMA pipe); and because
+// s - 1 == ~(~s + 1), the dead bytes are complemented on the way in and on the way out (folded into the masking
+// LOP3s), so that every byte that moves is incremented by that 0/1.  11 operations per 4 cells (the form with a
+// general bytewise addition of a +1 / -1 delta took 14, the two-test form 16); the kernel's time follows its
+// instruction count.
 CGL_HD uint32_t stable_update4_decay(uint32_t s, uint32_t surv_mask, uint32_t born_mask, uint32_t spawn4,
                                      uint32_t max4, uint32_t min4)
 {
@@ -164,13 +166,14 @@ CGL_HD uint32_t stable_update4_decay(uint32_t s, uint32_t surv_mask, uint32_t bo
     const uint32_t x = s ^ cmp;
     const uint32_t ne7 = (((x & L) + L) | x) & H;                                   // bit 7: s != its constant
 #if defined(__CUDA_ARCH__)
-    const uint32_t m = __umulhi(ne7, 1u << 25) * 255u;                              // bytes: 0xFF where it moves
+    const uint32_t e = __umulhi(ne7, 1u << 25);                                     // 0/1 per byte: the byte moves
 #else
-    const uint32_t m = (ne7 >> 7) * 255u;
+    const uint32_t e = ne7 >> 7;
 #endif
-    const uint32_t d = m & (~surv_mask | 0x01010101u);                              // +1 survivors, -1 (0xFF) dead
-    const uint32_t sum = ((s & L) + (d & L)) ^ ((s ^ d) & H);                       // bytewise s + d, wraps like int8
-    return (sum & ~born_mask) | (spawn4 & born_mask);
+    const uint32_t t = ((s ^ ~surv_mask) & L) + e;                                  // low 7 bits of (dead ? ~s : s) + e
+    // (dead ? ~s : s) + e, complemented back for dead bytes:  t ^ ((s ^ ~surv) & H) ^ ~surv  ==  t ^ (s & H) ^ (~surv & L)
+    const uint32_t r = (t ^ (s & H)) ^ (~surv_mask & L);
+    return (r & ~born_mask) | (spawn4 & born_mask);
 }
 
 // stable' for 4 cells with a dead-cell rule: surv_mask / born_mask are byte masks (0xFF) of the cells that
