@@ -365,6 +365,8 @@ extern "C" int cgl_sim_serve(const cgl_sim_step_args_t *a, const void *cmd_host,
     CGL_REQUIRE(a && cmd_host && a->world_a_dev && a->world_b_dev && a->stable_dev && a->result && a->side,
                 CGL_E_BADARG, "cgl_sim_serve: bad argument");
     CGL_REQUIRE(a->side <= SIM1_SERVE_MAX_SIDE, CGL_E_BADARG, "cgl_sim_serve: side must be <= %u", SIM1_SERVE_MAX_SIDE);
+    CGL_REQUIRE(((uintptr_t)a->result & 15u) == 0 && ((uintptr_t)a->obs_mirror & 15u) == 0 && ((uintptr_t)cmd_host & 7u) == 0,
+                CGL_E_BADARG, "cgl_sim_serve: result and obs_mirror must be 16-byte aligned, cmd_host 8-byte aligned");
     CGL_REQUIRE(a->dead_rule >= CGL_DEAD_ZERO && a->dead_rule <= CGL_DEAD_SAT && a->empty >= -128 && a->empty <= 127 &&
                     a->empty_min >= -128 && a->empty_min <= 127 && linger_us > 0 && linger_us <= 100000,
                 CGL_E_BADARG, "cgl_sim_serve: dead_rule must be 0..2, empty / empty_min must fit int8, linger 1..100000 us");

@@ -272,7 +272,8 @@ int cgl_sim_step_ex(const cgl_sim_step_args_t *args, int32_t action, uint32_t se
  *   cmd_host      pinned host-mapped uint64 the host writes with one store: (seq << 32) | action, action as in
  *                 cgl_sim_step, or CGL_SIM_QUIT to make the kernel leave.  A command is new when its seq differs
  *                 from the last one served (`last_seq` at launch).
- *   args->result  pinned host-mapped int32[8]: per served step ONE 16-byte store {reward, live cells, seq, 0}
+ *   args->result  pinned host-mapped int32[8], 16-byte aligned (so must args->obs_mirror be; cmd_host 8-byte
+ *                 aligned): per served step ONE 16-byte store {reward, live cells, seq, 0}
  *                 after the new observation is complete in args->obs_mirror (system-scope fence in between); when
  *                 the kernel has left -- planes written back to world_a/world_b (whichever held the state, see
  *                 flip_planes; not advanced) and stable_dev -- result[4] = launch_id.

@@ -47,6 +47,15 @@ def test_bad_arguments_are_reported_without_a_gpu():
     assert b"cgl_pack" in lib.cgl_last_error()
     with pytest.raises(native.CglNativeError):
         native.check(lib.cgl_env_step(None, None, None, 1, 8, None, -1, 1, None, None, None, None), "cgl_env_step")
+    # the resident single-env server refuses misaligned mailboxes and sides it cannot hold before touching the device
+    import ctypes
+    a = native.SimStepArgs()
+    a.world_a = a.world_b = a.stable = 0x1000
+    a.side, a.obs_mirror, a.result = 64, 0x2000, 0x3004
+    assert lib.cgl_sim_serve(ctypes.byref(a), 0x4000, 0, 1, 100, None) == native.E_BADARG and b"aligned" in lib.cgl_last_error()
+    a.result, a.side = 0x3000, 257
+    assert lib.cgl_sim_serve(ctypes.byref(a), 0x4000, 0, 1, 100, None) == native.E_BADARG and b"side" in lib.cgl_last_error()
+    assert lib.cgl_sim_serve_max_side() == 256
 
 
 def test_product_never_imports_the_oracle():
