@@ -193,6 +193,7 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
     }
     for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) stab[i] = stable[i];
     uint32_t done = last_seq;
+    unsigned long long t_seen = 0;                                 // (thread 0) when the current command was seen
     __syncthreads();
 
     for (;;) {
@@ -204,6 +205,7 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
                 if ((uint32_t)(c >> 32) != done) break;
                 if (globaltimer_ns() - t0 > linger_ns) { c = SIM1_QUIT; break; }
             }
+            t_seen = globaltimer_ns();
             const uint32_t action = (uint32_t)c;
             if (action < size) {                                   // toggle_state before the step
                 const uint32_t y = action / side, x = action - y * side;
@@ -262,6 +264,7 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
             atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
         }
         __syncthreads();
+        const unsigned long long t_step = threadIdx.x == 0 ? globaltimer_ns() : 0ull;
         // the observation: shared memory -> the caller's pinned mirror (16-byte posted writes), fenced by the writers
         if (obs_mirror != nullptr) {
             const uint32_t n16 = size >> 4;
@@ -277,9 +280,15 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
             if (stored) __threadfence_system();
             __syncthreads();
         }
-        if (threadIdx.x == 0)                                      // one 16-byte store: reward, alive and seq arrive together
+        if (threadIdx.x == 0) {
+            // diagnostics first (result[5..6]: ns from "command seen" to "step computed" / to "mirror fenced"), then
+            // one 16-byte store: reward, alive and seq arrive together
+            const unsigned long long t_pub = globaltimer_ns();
+            *reinterpret_cast<volatile int32_t *>(result + 5) = (int32_t)(t_step - t_seen);
+            *reinterpret_cast<volatile int32_t *>(result + 6) = (int32_t)(t_pub - t_seen);
             asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(result), "r"(red[0]), "r"(red[1]),
                          "r"((int)done), "r"(0) : "memory");
+        }
         uint8_t *tp = cur; cur = nxt; nxt = tp;
     }
 

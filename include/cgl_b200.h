@@ -276,7 +276,9 @@ int cgl_sim_step_ex(const cgl_sim_step_args_t *args, int32_t action, uint32_t se
  *                 aligned): per served step ONE 16-byte store {reward, live cells, seq, 0}
  *                 after the new observation is complete in args->obs_mirror (system-scope fence in between); when
  *                 the kernel has left -- planes written back to world_a/world_b (whichever held the state, see
- *                 flip_planes; not advanced) and stable_dev -- result[4] = launch_id.
+ *                 flip_planes; not advanced) and stable_dev -- result[4] = launch_id.  result[5] / result[6] are
+ *                 diagnostics of the last served step: nanoseconds from "command seen" to "step computed" and to
+ *                 "observation mirror fenced" on the device clock.
  *   linger_us     the kernel also leaves by itself after this long without a new command (1..100000), so a device-
  *                 wide synchronisation elsewhere in the process is never held up for longer; the host notices
  *                 result[4] == launch_id and launches again with the next step.

@@ -20,4 +20,8 @@ for side in (10, 64, 128, 200):
     for i in range(200, 200 + n):
         env.toggle_state(acts[i]); env.step(); n_state = env.get_stable(vector=True, shallow=True); total += env.reward()
     dt = time.perf_counter() - t0
-    print(json.dumps({"side": side, "env_steps_per_s": round(n / dt, 1), "us_per_step": round(dt / n * 1e6, 1), "reward_sum": int(total)}))
+    out = {"side": side, "env_steps_per_s": round(n / dt, 1), "us_per_step": round(dt / n * 1e6, 1), "reward_sum": int(total)}
+    if getattr(env, "_serving", False):                     # device-side share of the last served step (cgl_sim_serve)
+        out["device_ns_cmd_to_step_done"] = int(env._res[5])
+        out["device_ns_cmd_to_mirror_fenced"] = int(env._res[6])
+    print(json.dumps(out))
