@@ -17,6 +17,8 @@
 //     synchronising the stream.
 // One CTA owns the environment: world bits unpacked to one byte per cell in shared memory, any side up to
 // CGL_SIM1_MAX_SIDE, every dead-cell rule of cgl_bits.cuh.
+#include <stdlib.h>
+
 #include "cgl_internal.cuh"
 
 namespace cgl {
@@ -136,6 +138,7 @@ sim1_step_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ w
 // launches the kernel again.
 constexpr uint32_t SIM1_SERVE_MAX_SIDE = 256;    // two halo'd byte planes + the stability plane: 197 KB of shared memory
 constexpr uint32_t SIM1_QUIT = 0xFFFFFFFEu;
+constexpr uint32_t SERVE_COPY_THREADS = 32;      // threads that write (and fence) the observation mirror; CGL_SERVE_COPIERS overrides
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
 {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(1024)
 sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, int8_t spawn, int8_t stable_max,
                   int rule, int8_t empty, int8_t empty_min, int masked, int8_t *obs_mirror, int32_t *result,
                   const unsigned long long *cmd, uint32_t last_seq, uint32_t launch_id, unsigned long long linger_ns,
-                  uint32_t tpr, uint32_t rows_per_pass)
+                  uint32_t tpr, uint32_t rows_per_pass, uint32_t copy_threads)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const uint32_t size = side * side, n_words = side * W, S = serve_stride(side);
@@ -268,16 +271,13 @@ sim1_serve_kernel(uint32_t *world, int8_t *stable, uint32_t side, uint32_t W, in
         // the observation: shared memory -> the caller's pinned mirror (16-byte posted writes), fenced by the writers
         if (obs_mirror != nullptr) {
             const uint32_t n16 = size >> 4;
-            bool stored = false;
-            for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
-                reinterpret_cast<uint4 *>(obs_mirror)[i] = reinterpret_cast<const uint4 *>(stab)[i];
-                stored = true;
+            const uint32_t copiers = n16 < copy_threads ? (n16 ? n16 : 1u) : copy_threads;
+            if (threadIdx.x < copiers) {
+                for (uint32_t i = threadIdx.x; i < n16; i += copiers)
+                    reinterpret_cast<uint4 *>(obs_mirror)[i] = reinterpret_cast<const uint4 *>(stab)[i];
+                for (uint32_t i = (n16 << 4) + threadIdx.x; i < size; i += copiers) obs_mirror[i] = stab[i];
+                __threadfence_system();
             }
-            for (uint32_t i = (n16 << 4) + threadIdx.x; i < size; i += blockDim.x) {
-                obs_mirror[i] = stab[i];
-                stored = true;
-            }
-            if (stored) __threadfence_system();
             __syncthreads();
         }
         if (threadIdx.x == 0) {
@@ -389,11 +389,19 @@ extern "C" int cgl_sim_serve(const cgl_sim_step_args_t *a, const void *cmd_host,
     if (rows_per_pass > side) rows_per_pass = side;
     const unsigned threads = (tpr * rows_per_pass + 31) / 32 * 32;
     const size_t smem = serve_smem_bytes(side);
+    static int copiers_knob = -1;                // CGL_SERVE_COPIERS: threads that write + fence the observation mirror (tuning)
+    if (copiers_knob < 0) {
+        const char *v = getenv("CGL_SERVE_COPIERS");
+        copiers_knob = v ? atoi(v) : 0;
+    }
+    uint32_t copy_threads = copiers_knob > 0 ? (uint32_t)copiers_knob : SERVE_COPY_THREADS;
+    if (copy_threads > threads) copy_threads = threads;
     const bool flip = (a->flip_planes != nullptr) && (*a->flip_planes & 1u);
     sim1_serve_kernel<<<1, threads, smem, as_stream(stream)>>>(
         flip ? a->world_b_dev : a->world_a_dev, a->stable_dev, side, W, (int8_t)a->spawn, (int8_t)a->stable_max,
         a->dead_rule, (int8_t)a->empty, (int8_t)a->empty_min, a->masked_toggle, a->obs_mirror, a->result,
-        static_cast<const unsigned long long *>(cmd_host), last_seq, launch_id, 1000ull * linger_us, tpr, rows_per_pass);
+        static_cast<const unsigned long long *>(cmd_host), last_seq, launch_id, 1000ull * linger_us, tpr, rows_per_pass,
+        copy_threads);
     CGL_LAUNCH_CHECK();
     return 0;
 }
