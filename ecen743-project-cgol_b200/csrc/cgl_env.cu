@@ -574,6 +574,55 @@ __global__ void pack_kernel(const uint8_t *__restrict__ cells, uint32_t *__restr
     }
 }
 
+// Rows of whole words (cols % 32 == 0: every fused side, every large grid): the cell index IS the bit index, so the
+// conversions are flat streams.  pack: a thread turns 32 cell bytes (two 16-byte loads) into one word -- "byte != 0"
+// lands in bit 7 of each byte, a multiply gathers the four bits of a word into a nibble.  HBM-bound: 1 + 1/8 bytes
+// per cell instead of one 32-byte request and one ballot per 32 cells.
+__global__ void __launch_bounds__(256)
+pack_words_kernel(const uint4 *__restrict__ cells16, uint32_t *__restrict__ world, uint64_t total_words)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total_words;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(cells16 + 2 * i), b = __ldg(cells16 + 2 * i + 1);
+        const uint32_t in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = in[k];
+            const uint32_t nz = ((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u) >> 7;      // 0/1 per byte
+            word |= ((nz * 0x10204080u) >> 28) << (4 * k);           // byte j of the group -> bit j of the nibble
+        }
+        world[i] = word;
+    }
+}
+
+// unpack / init_stable for rows of whole words: a thread expands 16 bits into one 16-byte store.
+// mode 0: cells = bit.  mode 1: stable = bit ? spawn : 0, zeros then replaced by `empty`.
+__global__ void __launch_bounds__(256)
+unpack_words_kernel(const uint32_t *__restrict__ world, uint4 *__restrict__ cells16, uint64_t total16, int mode,
+                    uint32_t spawn4, uint32_t empty4)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total16;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t half = (__ldg(world + (i >> 1)) >> ((i & 1) * 16)) & 0xffffu;
+        uint32_t out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t ones = (((half >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;        // 0/1 per byte
+            if (mode == 0) {
+                out[k] = ones;
+            } else {
+                const uint32_t m = ones * 0xffu;
+                const uint32_t v = m & spawn4;                         // alive ? spawn : 0 ...
+                // ... and every byte that is 0 now (dead cells, or alive with spawn == 0) becomes `empty`
+                const uint32_t nz = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
+                out[k] = v | (empty4 & ~((nz >> 7) * 0xffu));
+            }
+        }
+        cells16[i] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
+
 // One thread per cell.  mode 0: cells = bit.  mode 1: stable = bit ? spawn : 0, zeros then replaced by
 // `empty` (CGL/CGL.py:111-112; the fork's `stable[stable == 0] = empty`, CGL_action+/CGL.py:124-126).
 __global__ void unpack_kernel(const uint32_t *__restrict__ world, uint8_t *__restrict__ cells,
@@ -673,7 +722,11 @@ extern "C" int cgl_pack(const uint8_t *cells, uint32_t *world, uint64_t n_envs, 
     CGL_REQUIRE(cells && world && n_envs && rows && cols, CGL_E_BADARG, "cgl_pack: bad argument");
     const uint32_t W = cgl_words_per_row(cols);
     const uint64_t words = n_envs * rows * W;
-    pack_kernel<<<grid_for(words, 256), 256, 0, as_stream(stream)>>>(cells, world, n_envs, rows, cols, W);
+    if (cols % 32 == 0 && (reinterpret_cast<uintptr_t>(cells) & 15u) == 0)
+        pack_words_kernel<<<grid_for(words, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(cells),
+                                                                                world, words);
+    else
+        pack_kernel<<<grid_for(words, 256), 256, 0, as_stream(stream)>>>(cells, world, n_envs, rows, cols, W);
     CGL_LAUNCH_CHECK();
     return 0;
 }
@@ -683,8 +736,12 @@ extern "C" int cgl_unpack(const uint32_t *world, uint8_t *cells, uint64_t n_envs
 {
     CGL_REQUIRE(cells && world && n_envs && rows && cols, CGL_E_BADARG, "cgl_unpack: bad argument");
     const uint64_t total = n_envs * rows * cols;
-    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        world, cells, n_envs, rows, cols, cgl_words_per_row(cols), 0, 0);
+    if (cols % 32 == 0 && (reinterpret_cast<uintptr_t>(cells) & 15u) == 0)
+        unpack_words_kernel<<<grid_for(total / 16, 256), 256, 0, as_stream(stream)>>>(
+            world, reinterpret_cast<uint4 *>(cells), total / 16, 0, 0u, 0u);
+    else
+        unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+            world, cells, n_envs, rows, cols, cgl_words_per_row(cols), 0, 0);
     CGL_LAUNCH_CHECK();
     return 0;
 }
@@ -694,9 +751,13 @@ extern "C" int cgl_init_stable(const uint32_t *world, int8_t *stable, uint64_t n
 {
     CGL_REQUIRE(stable && world && n_envs && side, CGL_E_BADARG, "cgl_init_stable: bad argument");
     const uint64_t total = n_envs * side * side;
-    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
-        (uint8_t)(int8_t)spawn);
+    if (side % 32 == 0 && (reinterpret_cast<uintptr_t>(stable) & 15u) == 0)
+        unpack_words_kernel<<<grid_for(total / 16, 256), 256, 0, as_stream(stream)>>>(
+            world, reinterpret_cast<uint4 *>(stable), total / 16, 1, rep4(spawn), 0u);
+    else
+        unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+            world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
+            (uint8_t)(int8_t)spawn);
     CGL_LAUNCH_CHECK();
     return 0;
 }
@@ -730,9 +791,13 @@ extern "C" int cgl_init_stable_rule(const uint32_t *world, int8_t *stable, uint6
 {
     CGL_REQUIRE(stable && world && n_envs && side, CGL_E_BADARG, "cgl_init_stable_rule: bad argument");
     const uint64_t total = n_envs * side * side;
-    unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
-        (uint8_t)(int8_t)spawn, (uint8_t)(int8_t)empty);
+    if (side % 32 == 0 && (reinterpret_cast<uintptr_t>(stable) & 15u) == 0)
+        unpack_words_kernel<<<grid_for(total / 16, 256), 256, 0, as_stream(stream)>>>(
+            world, reinterpret_cast<uint4 *>(stable), total / 16, 1, rep4(spawn), rep4(empty));
+    else
+        unpack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+            world, reinterpret_cast<uint8_t *>(stable), n_envs, side, side, cgl_words_per_row(side), 1,
+            (uint8_t)(int8_t)spawn, (uint8_t)(int8_t)empty);
     CGL_LAUNCH_CHECK();
     return 0;
 }

@@ -462,3 +462,40 @@ def test_checkpoint_resume_continues_bit_for_bit(cgl, tmp_path, kw):
     with pytest.raises(ValueError):
         np.savez(str(tmp_path / "bad.npz"), format=np.array("something else"))
         BatchedSim.load_checkpoint(str(tmp_path / "bad.npz"))
+
+
+@pytest.mark.parametrize("rows,cols,n_envs", [(128, 128, 7), (64, 64, 33), (3, 4096, 2), (37, 160, 5), (50, 50, 3), (9, 33, 4)])
+def test_pack_unpack_and_initial_stability_at_the_api_boundary(cgl, rows, cols, n_envs):
+    """cgl_pack / cgl_unpack / cgl_init_stable(_rule): the whole-word fast kernels (cols % 32 == 0, 16-byte aligned
+    buffers), the same data through a misaligned view (generic kernels), and ragged widths -- against numpy.
+    Cells arrive as arbitrary bytes: nonzero = alive (CGL/CGL.py:94,107,111-112; fork: CGL_action+/CGL.py:122-126)."""
+    import torch
+    from cgl_b200 import native
+    lib = native.load()
+    rs = np.random.RandomState(rows * 1000 + cols)
+    cells = (rs.randint(0, 4, size=(n_envs, rows * cols)) * rs.randint(1, 64, size=(n_envs, rows * cols))).astype(np.uint8)
+    alive = (cells != 0).astype(np.uint8)
+    W = (cols + 31) // 32
+    st = native.current_stream()
+    for misalign in (0, 1):
+        raw = torch.zeros(cells.size + 16, dtype=torch.uint8, device="cuda")
+        c_d = raw[misalign:misalign + cells.size]
+        c_d.copy_(torch.from_numpy(cells.reshape(-1)))
+        world = torch.zeros(n_envs * rows * W, dtype=torch.int32, device="cuda")
+        native.check(lib.cgl_pack(native.dptr(c_d), native.dptr(world), n_envs, rows, cols, st))
+        out_raw = torch.full((cells.size + 16,), 7, dtype=torch.uint8, device="cuda")
+        out = out_raw[misalign:misalign + cells.size]
+        native.check(lib.cgl_unpack(native.dptr(world), native.dptr(out), n_envs, rows, cols, st))
+        assert np.array_equal(out.cpu().numpy().reshape(n_envs, -1), alive), (rows, cols, misalign)
+        assert int(out_raw[misalign + cells.size:].min()) == 7 and (misalign == 0 or int(out_raw[0]) == 7)
+        if rows == cols:
+            for spawn, empty in ((-2, 0), (0, -3), (5, -1), (-128, 127)):
+                s_raw = torch.zeros(cells.size + 16, dtype=torch.int8, device="cuda")
+                s_d = s_raw[misalign:misalign + cells.size]
+                native.check(lib.cgl_init_stable_rule(native.dptr(world), native.dptr(s_d), n_envs, rows, spawn, empty, st))
+                want = np.where(alive == 1, np.int8(spawn), np.int8(0)).astype(np.int8)
+                want[want == 0] = np.int8(empty)
+                assert np.array_equal(s_d.cpu().numpy().reshape(n_envs, -1), want), (rows, spawn, empty, misalign)
+                native.check(lib.cgl_init_stable(native.dptr(world), native.dptr(s_d), n_envs, rows, spawn, st))
+                assert np.array_equal(s_d.cpu().numpy().reshape(n_envs, -1),
+                                      np.where(alive == 1, np.int8(spawn), np.int8(0))), (rows, spawn, misalign)
