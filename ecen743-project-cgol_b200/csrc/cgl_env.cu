@@ -391,6 +391,31 @@ static bool pdl_enabled()
     return v != 0 && !g_pdl_suppress;
 }
 
+// CGL_ENV_BYTES=0 sends the sides the fused kernel does not take through the three generic kernels again (tests
+// force both paths; tuning).
+static bool env_bytes_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CGL_ENV_BYTES");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// Sides the one-launch byte-plane kernel (env_step_bytes_kernel, below) takes.  CGL_ENV_BYTES=2 forces it for every
+// side up to 256 (tests).
+static bool env_bytes_takes(uint32_t side)
+{
+    if (!env_bytes_enabled() || side > 256) return false;
+    static int force = -1;
+    if (force < 0) {
+        const char *e = getenv("CGL_ENV_BYTES");
+        force = (e && e[0] == '2') ? 1 : 0;
+    }
+    return force || side >= 32;
+}
+
 template <int S>
 static int launch_env_fused(const cgl_env_step_args_t &a, cudaStream_t st)
 {
@@ -541,6 +566,186 @@ __global__ void stable_generic_kernel(const uint32_t *__restrict__ prev, const u
             if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(reward_out + e, sum);
         }
     }
+}
+
+// =========================================================================================
+// Any side up to ENV_BYTES_MAX_SIDE in ONE launch: one CTA per env, the world as one byte per cell in shared memory
+// with torus halos (rows of `stride` bytes: left halo at byte 3, cell x at byte 4 + x, right halo at byte 4 + side,
+// every other byte 0; halo rows above and below), so that a thread's four cells and their neighbours are three
+// aligned words plus six bytes whatever the side is, the generation is packed-byte arithmetic (life_next4_bytes)
+// and the stability update is the 4-cells-per-word rule of the fused kernel.  ~50 instructions per 4 cells against
+// ~20 in the fused kernel (which needs side % 32 == 0), but one pass over HBM instead of three kernels with a scalar
+// rule per cell.  Measured against the three-kernel path, us per step: 1024 x 200^2 66 vs 306, 4096 x 100^2 76 vs 253,
+// 2048 x 130^2 118 vs 230, 16384 x 50^2 189 vs 251 (sides that are not multiples of 4 pay byte accesses to the
+// stability plane); instruction-bound (181 thread instructions per 4 cells, issue slots 71 % busy), so sides below 32
+// -- several envs per CTA, little work per thread -- stay on the small kernels.
+// =========================================================================================
+constexpr uint32_t ENV_BYTES_MAX_SIDE = 256;
+constexpr uint32_t ENV_BYTES_MIN_SIDE = 32;      // below that the three small kernels win (measured: side 10, 65536 envs: 55 vs 68 us)
+constexpr int ENV_BYTES_THREADS = 256;
+
+__host__ __device__ __forceinline__ uint32_t env_bytes_stride(uint32_t side) { return (side + 5u + 3u) & ~3u; }
+
+__global__ void __launch_bounds__(ENV_BYTES_THREADS)
+env_step_bytes_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out, const int8_t *stable_in,
+                      int8_t *stable_out, uint32_t side, uint32_t W, const int32_t *__restrict__ actions, int8_t spawn,
+                      uint32_t max4, uint32_t min4, uint32_t empty4, int rule, int masked,
+                      int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out, int *__restrict__ err_flag,
+                      uint32_t tpr, uint32_t rows_per_pass, uint32_t n_envs, uint32_t slot_threads, uint32_t slots,
+                      uint32_t slot_bytes)
+{
+    // Small sides: several envs per CTA, one SLOT of slot_threads (a multiple of 32) threads each, its own piece of
+    // shared memory; every slot runs the same trip counts, so the barriers stay CTA-wide.
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const uint32_t size = side * side, n_words = side * W, S = env_bytes_stride(side);
+    const uint32_t slot = threadIdx.x / slot_threads, tid = threadIdx.x - slot * slot_threads;
+    const uint32_t e_raw = blockIdx.x * slots + slot;
+    const bool env_ok = slot < slots && e_raw < n_envs;
+    const uint32_t e = env_ok ? e_raw : 0u;
+    uint8_t *plane = smem_dyn + (slot < slots ? slot : 0u) * slot_bytes;
+    uint32_t *nw = reinterpret_cast<uint32_t *>(plane + (((side + 2) * S + 15u) & ~15u));         // next world, packed
+    __shared__ int red_all[2 * (ENV_BYTES_THREADS / 32)];
+    int *red = red_all + 2 * (slot < slots ? slot : 0u);
+    const uint32_t *win = world_in + (size_t)e * n_words;
+    const size_t sbase = (size_t)e * size;
+
+    // toggle_state before the step (CGL/main.py:66-67): applied to the packed words as they are loaded
+    int act = -1;
+    if (actions != nullptr && env_ok) {
+        const int a = actions[e];
+        if (a >= 0 && (uint32_t)a < size) act = a;
+        else if ((uint32_t)a != size && tid == 0) {
+            if (err_flag != nullptr) atomicOr(err_flag, 1);
+            raise_alarm(ALARM_BAD_ACTION);
+        }
+    }
+    const uint32_t act_y = act >= 0 ? (uint32_t)act / side : 0xffffffffu;
+    const uint32_t act_x = act >= 0 ? (uint32_t)act - act_y * side : 0u;
+    auto load_word = [&](uint32_t y, uint32_t w) {
+        uint32_t v = __ldg(win + y * W + w);
+        if (y == act_y && w == (act_x >> 5)) v ^= 1u << (act_x & 31);
+        return v;
+    };
+
+    if (tid == 0 && env_ok) { red[0] = 0; red[1] = 0; }
+    // world bits -> byte plane; the thread that handles a row's first / last word also writes the row's halos, and
+    // the first / last row is written a second time as the halo row below / above the grid
+    for (uint32_t i = tid; i < n_words && env_ok; i += slot_threads) {
+        nw[i] = 0;
+        const uint32_t y = i / W, w = i - y * W;
+        const uint32_t bits = load_word(y, w);
+        const uint32_t cells_here = side - 32 * w < 32 ? side - 32 * w : 32;
+        const uint32_t groups = (cells_here + 3) >> 2;
+        const uint32_t last_bit = (load_word(y, W - 1) >> ((side - 1) & 31)) & 1u;    // cell side-1 of the row
+        const uint32_t first_bit = load_word(y, 0) & 1u;
+        for (int image = 0; image < 3; ++image) {
+            if (image == 1 && y != 0) continue;                   // row 0 again as the halo row below the grid
+            if (image == 2 && y != side - 1) continue;            // row side-1 again as the halo row above it
+            uint8_t *row = plane + (image == 0 ? y + 1 : (image == 1 ? side + 1 : 0)) * S;
+            for (uint32_t g = 0; g < groups; ++g)
+                *reinterpret_cast<uint32_t *>(row + 4 + 32 * w + 4 * g) = (((bits >> (4 * g)) & 0xfu) * 0x00204081u) & 0x01010101u;
+            if (w == 0) *reinterpret_cast<uint32_t *>(row) = last_bit << 24;                  // pads 0..2 and the left halo
+            if (w == W - 1) {                                                                 // right halo, then pads
+                row[4 + side] = (uint8_t)first_bit;
+                for (uint32_t b = 4 + side + 1; b < S; ++b) row[b] = 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t ty = tid / tpr, x0 = (tid - ty * tpr) * 4;
+    const bool lane_ok = ty < rows_per_pass && env_ok;
+    const uint32_t nx = side - x0 < 4 ? side - x0 : 4;
+    const uint32_t valid = nx == 4 ? 0xffffffffu : ((1u << (8 * nx)) - 1u);
+    const bool vec = (side & 3u) == 0;                            // then size % 16 == 0: every env's rows are word-aligned
+    const uint32_t spawn4 = rep4(spawn);
+    int acc = 0;
+    uint32_t pop = 0;
+    auto load_sv = [&](uint32_t y) {
+        const uint32_t base = y * side + x0;
+        uint32_t sv = 0;
+        if (vec) sv = *reinterpret_cast<const uint32_t *>(stable_in + sbase + base);
+        else for (uint32_t k = 0; k < nx; ++k) sv |= (uint32_t)(uint8_t)stable_in[sbase + base + k] << (8 * k);
+        return sv;
+    };
+    auto step_row = [&](uint32_t y, uint32_t sv) {
+        const uint8_t *rm = plane + (y + 1) * S + 4 + x0;                                     // 4-byte aligned
+        const uint32_t u = *reinterpret_cast<const uint32_t *>(rm - S);
+        const uint32_t m = *reinterpret_cast<const uint32_t *>(rm);
+        const uint32_t d = *reinterpret_cast<const uint32_t *>(rm + S);
+        const uint32_t lc = (uint32_t)rm[-(int)S - 1] + rm[-1] + rm[S - 1];
+        const uint32_t rc = (uint32_t)rm[4 - (int)S] + rm[4] + rm[S + 4];
+        const uint32_t q = life_next4_bytes(u, m, d, lc, rc) & valid;                           // alive next, 0/1 per byte
+        const uint32_t mv = m & valid;
+        const uint32_t base = y * side + x0;
+        if (y == act_y && act_x - x0 < nx) {                      // stable[action] = spawn (fork: 0 if toggled to dead)
+            const uint32_t k = act_x - x0;
+            const uint32_t alive_now = (mv >> (8 * k)) & 1u;
+            const uint32_t put = (masked && !alive_now) ? 0u : (uint32_t)(uint8_t)spawn;
+            sv = (sv & ~(0xffu << (8 * k))) | (put << (8 * k));
+        }
+        const uint32_t out = stable_update4_rule(rule, sv, (q & mv) * 255u, (q & ~mv) * 255u, spawn4, max4, min4,
+                                                 empty4) & valid;
+        acc = __dp4a((int)out, 0x01010101, acc);
+        pop += __popc(q);
+        const uint32_t nib = (q * 0x10204080u) >> 28;             // byte j -> bit j
+        if (nib) atomicOr(&nw[y * W + (x0 >> 5)], nib << (x0 & 31));
+        if (vec) *reinterpret_cast<uint32_t *>(stable_out + sbase + base) = out;
+        else for (uint32_t k = 0; k < nx; ++k) stable_out[sbase + base + k] = (int8_t)(out >> (8 * k));
+    };
+    // a thread's rows are ty, ty + rows_per_pass, ...: the stability words of FOUR of them are requested before the
+    // first is used (a CTA's life is latency: one dependent HBM access per row otherwise)
+    constexpr int U = 4;
+    if (lane_ok)
+        for (uint32_t y0 = ty; y0 < side; y0 += U * rows_per_pass) {
+            uint32_t svs[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+                if (y0 + k * rows_per_pass < side) svs[k] = load_sv(y0 + k * rows_per_pass);
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+                if (y0 + k * rows_per_pass < side) step_row(y0 + k * rows_per_pass, svs[k]);
+        }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    pop = __reduce_add_sync(0xffffffffu, pop);
+    if ((threadIdx.x & 31) == 0 && env_ok) {
+        atomicAdd(&red[0], acc);
+        atomicAdd(reinterpret_cast<unsigned *>(&red[1]), pop);
+    }
+    __syncthreads();
+    uint32_t *wout = world_out + (size_t)e * n_words;
+    for (uint32_t i = tid; i < n_words && env_ok; i += slot_threads) wout[i] = nw[i];
+    if (tid == 0 && env_ok) {
+        if (reward_out != nullptr) reward_out[e] = red[0];
+        if (alive_out != nullptr) alive_out[e] = (uint32_t)red[1];
+    }
+}
+
+static size_t env_bytes_smem(uint32_t side)
+{
+    const size_t b = ((((size_t)side + 2) * env_bytes_stride(side) + 15u) & ~(size_t)15u) + 4 * (size_t)side * cgl_words_per_row(side);
+    return (b + 15u) & ~(size_t)15u;
+}
+
+static int launch_env_bytes(const cgl_env_step_args_t &a, cudaStream_t st)
+{
+    static PerDeviceOnce once;
+    if (once.first())
+        CGL_CUDA(cudaFuncSetAttribute(env_step_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)env_bytes_smem(ENV_BYTES_MAX_SIDE)));
+    const uint32_t side = a.side, W = cgl_words_per_row(side), tpr = (side + 3) / 4;
+    uint32_t rows_per_pass = ENV_BYTES_THREADS / tpr;             // tpr <= 64
+    if (rows_per_pass > side) rows_per_pass = side;
+    const uint32_t slot_threads = (tpr * rows_per_pass + 31) / 32 * 32;       // threads of one env, warp-aligned
+    const uint32_t slots = ENV_BYTES_THREADS / slot_threads;                  // envs per CTA (1 for side >= 23)
+    const uint32_t slot_bytes = (uint32_t)env_bytes_smem(side);
+    const unsigned grid = (unsigned)((a.n_envs + slots - 1) / slots);
+    env_step_bytes_kernel<<<grid, ENV_BYTES_THREADS, (size_t)slots * slot_bytes, st>>>(
+        a.world_in_dev, a.world_out_dev, a.stable_in_dev, a.stable_out_dev, side, W, a.actions_dev, (int8_t)a.spawn,
+        rep4(a.stable_max), rep4(a.empty_min), rep4(a.empty), a.dead_rule, a.masked_toggle != 0, a.reward_out_dev,
+        a.alive_out_dev, a.err_flag_dev, tpr, rows_per_pass, (uint32_t)a.n_envs, slot_threads, slots, slot_bytes);
+    CGL_LAUNCH_CHECK();
+    return 0;
 }
 
 // =========================================================================================
@@ -713,7 +918,8 @@ extern "C" int cgl_env_step_is_fused(uint32_t side) { return side % 32 == 0 && s
 
 extern "C" int cgl_env_step_launches(uint32_t side, int has_actions)
 {
-    return cgl_env_step_is_fused(side) ? 1 : (2 + (has_actions ? 1 : 0));
+    if (cgl_env_step_is_fused(side) || env_bytes_takes(side)) return 1;
+    return 2 + (has_actions ? 1 : 0);
 }
 
 extern "C" int cgl_pack(const uint8_t *cells, uint32_t *world, uint64_t n_envs, uint32_t rows,
@@ -874,8 +1080,10 @@ extern "C" int cgl_env_step_ex(const cgl_env_step_args_t *args, cgl_stream_t str
         case 256: rc = launch_env_fused<256>(a, st); break;
         }
     }
+    if (rc == -100 && env_bytes_takes(a.side))
+        rc = launch_env_bytes(a, st);                // any side up to 256: one launch, one CTA per env
     if (rc == -100) {
-        // generic sides: (plane copy) -> toggle -> generation -> stability, all in place on stable_out
+        // larger sides: (plane copy) -> toggle -> generation -> stability, all in place on stable_out
         const uint32_t W = cgl_words_per_row(a.side);
         const uint64_t cells = a.n_envs * a.side * a.side;
         if (a.stable_in_dev != a.stable_out_dev)

@@ -353,7 +353,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
 from cgl_b200.batched import BatchedSim
 from oracle import oracle
-for side, n in ((128, 9), (64, 37), (32, 70)):
+for side, n in ((128, 9), (64, 37), (32, 70), (10, 40), (33, 9), (50, 21), (100, 6), (131, 3), (200, 4), (1, 5), (3, 7)):
     size = side * side
     rs = np.random.RandomState(side)
     cells = rs.randint(2, size=(n, size)).astype(np.uint8)
@@ -374,9 +374,10 @@ print("variant ok")
 
 @pytest.mark.parametrize("knobs", [{"CGL_ENV_IMPL": "tma", "CGL_ENV_TMA_THREADS": "256"},
                                    {"CGL_ENV_IMPL": "tma", "CGL_ENV_TMA_THREADS": "128"},
-                                   {"CGL_ENV_PDL": "0"}])
+                                   {"CGL_ENV_PDL": "0"}, {"CGL_ENV_BYTES": "0"}, {"CGL_ENV_BYTES": "2"}])
 def test_env_kernel_variants_vs_oracle(cgl, knobs):
-    """The persistent bulk-copy (cp.async.bulk + mbarrier) kernel and the non-PDL launch path."""
+    """The persistent bulk-copy (cp.async.bulk + mbarrier) kernel, the non-PDL launch path, and -- on sides the fused
+    kernel does not take -- the one-launch byte-plane kernel against the three generic kernels it replaced."""
     import subprocess
     import sys
     from conftest import PKG
