@@ -575,8 +575,8 @@ __global__ void stable_generic_kernel(const uint32_t *__restrict__ prev, const u
 // aligned words plus six bytes whatever the side is, the generation is packed-byte arithmetic (life_next4_bytes)
 // and the stability update is the 4-cells-per-word rule of the fused kernel.  ~50 instructions per 4 cells against
 // ~20 in the fused kernel (which needs side % 32 == 0), but one pass over HBM instead of three kernels with a scalar
-// rule per cell.  Measured against the three-kernel path, us per step: 1024 x 200^2 66 vs 306, 4096 x 100^2 76 vs 253,
-// 2048 x 130^2 118 vs 230, 16384 x 50^2 189 vs 251 (sides that are not multiples of 4 pay byte accesses to the
+// rule per cell.  Measured against the three-kernel path, us per step: 1024 x 200^2 63 vs 306, 4096 x 100^2 66 vs 253,
+// 2048 x 130^2 109 vs 230, 16384 x 50^2 158 vs 251 (sides that are not multiples of 4 pay byte accesses to the
 // stability plane); instruction-bound (181 thread instructions per 4 cells, issue slots 71 % busy), so sides below 32
 // -- several envs per CTA, little work per thread -- stay on the small kernels.
 // =========================================================================================
@@ -586,10 +586,13 @@ constexpr int ENV_BYTES_THREADS = 256;
 
 __host__ __device__ __forceinline__ uint32_t env_bytes_stride(uint32_t side) { return (side + 5u + 3u) & ~3u; }
 
+// VEC: side % 4 == 0 (then side^2 % 16 == 0: every row of every env's stability plane is word-aligned); RULE: the
+// dead-cell rule, compile-time like in the fused kernel.
+template <bool VEC, int RULE>
 __global__ void __launch_bounds__(ENV_BYTES_THREADS)
 env_step_bytes_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restrict__ world_out, const int8_t *stable_in,
                       int8_t *stable_out, uint32_t side, uint32_t W, const int32_t *__restrict__ actions, int8_t spawn,
-                      uint32_t max4, uint32_t min4, uint32_t empty4, int rule, int masked,
+                      uint32_t max4, uint32_t min4, uint32_t empty4, int masked,
                       int32_t *__restrict__ reward_out, uint32_t *__restrict__ alive_out, int *__restrict__ err_flag,
                       uint32_t tpr, uint32_t rows_per_pass, uint32_t n_envs, uint32_t slot_threads, uint32_t slots,
                       uint32_t slot_bytes)
@@ -636,8 +639,9 @@ env_step_bytes_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
         const uint32_t bits = load_word(y, w);
         const uint32_t cells_here = side - 32 * w < 32 ? side - 32 * w : 32;
         const uint32_t groups = (cells_here + 3) >> 2;
-        const uint32_t last_bit = (load_word(y, W - 1) >> ((side - 1) & 31)) & 1u;    // cell side-1 of the row
-        const uint32_t first_bit = load_word(y, 0) & 1u;
+        // the row's halos: cell side-1 left of cell 0 (written with word 0), cell 0 right of cell side-1 (last word)
+        const uint32_t last_bit = w == 0 ? (load_word(y, W - 1) >> ((side - 1) & 31)) & 1u : 0u;
+        const uint32_t first_bit = w == W - 1 ? load_word(y, 0) & 1u : 0u;
         for (int image = 0; image < 3; ++image) {
             if (image == 1 && y != 0) continue;                   // row 0 again as the halo row below the grid
             if (image == 2 && y != side - 1) continue;            // row side-1 again as the halo row above it
@@ -657,7 +661,7 @@ env_step_bytes_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
     const bool lane_ok = ty < rows_per_pass && env_ok;
     const uint32_t nx = side - x0 < 4 ? side - x0 : 4;
     const uint32_t valid = nx == 4 ? 0xffffffffu : ((1u << (8 * nx)) - 1u);
-    const bool vec = (side & 3u) == 0;                            // then size % 16 == 0: every env's rows are word-aligned
+    constexpr bool vec = VEC;
     const uint32_t spawn4 = rep4(spawn);
     int acc = 0;
     uint32_t pop = 0;
@@ -684,7 +688,7 @@ env_step_bytes_kernel(const uint32_t *__restrict__ world_in, uint32_t *__restric
             const uint32_t put = (masked && !alive_now) ? 0u : (uint32_t)(uint8_t)spawn;
             sv = (sv & ~(0xffu << (8 * k))) | (put << (8 * k));
         }
-        const uint32_t out = stable_update4_rule(rule, sv, (q & mv) * 255u, (q & ~mv) * 255u, spawn4, max4, min4,
+        const uint32_t out = stable_update4_rule(RULE, sv, (q & mv) * 255u, (q & ~mv) * 255u, spawn4, max4, min4,
                                                  empty4) & valid;
         acc = __dp4a((int)out, 0x01010101, acc);
         pop += __popc(q);
@@ -730,9 +734,13 @@ static size_t env_bytes_smem(uint32_t side)
 static int launch_env_bytes(const cgl_env_step_args_t &a, cudaStream_t st)
 {
     static PerDeviceOnce once;
-    if (once.first())
-        CGL_CUDA(cudaFuncSetAttribute(env_step_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)env_bytes_smem(ENV_BYTES_MAX_SIDE)));
+    if (once.first()) {
+        const int cap = (int)env_bytes_smem(ENV_BYTES_MAX_SIDE);
+#define CGL_ATTR(V, R) CGL_CUDA(cudaFuncSetAttribute(env_step_bytes_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap))
+        CGL_ATTR(true, CGL_DEAD_ZERO); CGL_ATTR(true, CGL_DEAD_DECAY); CGL_ATTR(true, CGL_DEAD_SAT);
+        CGL_ATTR(false, CGL_DEAD_ZERO); CGL_ATTR(false, CGL_DEAD_DECAY); CGL_ATTR(false, CGL_DEAD_SAT);
+#undef CGL_ATTR
+    }
     const uint32_t side = a.side, W = cgl_words_per_row(side), tpr = (side + 3) / 4;
     uint32_t rows_per_pass = ENV_BYTES_THREADS / tpr;             // tpr <= 64
     if (rows_per_pass > side) rows_per_pass = side;
@@ -740,10 +748,16 @@ static int launch_env_bytes(const cgl_env_step_args_t &a, cudaStream_t st)
     const uint32_t slots = ENV_BYTES_THREADS / slot_threads;                  // envs per CTA (1 for side >= 23)
     const uint32_t slot_bytes = (uint32_t)env_bytes_smem(side);
     const unsigned grid = (unsigned)((a.n_envs + slots - 1) / slots);
-    env_step_bytes_kernel<<<grid, ENV_BYTES_THREADS, (size_t)slots * slot_bytes, st>>>(
-        a.world_in_dev, a.world_out_dev, a.stable_in_dev, a.stable_out_dev, side, W, a.actions_dev, (int8_t)a.spawn,
-        rep4(a.stable_max), rep4(a.empty_min), rep4(a.empty), a.dead_rule, a.masked_toggle != 0, a.reward_out_dev,
-        a.alive_out_dev, a.err_flag_dev, tpr, rows_per_pass, (uint32_t)a.n_envs, slot_threads, slots, slot_bytes);
+#define CGL_BYTES(V, R)                                                                                              \
+    env_step_bytes_kernel<V, R><<<grid, ENV_BYTES_THREADS, (size_t)slots * slot_bytes, st>>>(                          \
+        a.world_in_dev, a.world_out_dev, a.stable_in_dev, a.stable_out_dev, side, W, a.actions_dev, (int8_t)a.spawn,   \
+        rep4(a.stable_max), rep4(a.empty_min), rep4(a.empty), a.masked_toggle != 0, a.reward_out_dev, a.alive_out_dev, \
+        a.err_flag_dev, tpr, rows_per_pass, (uint32_t)a.n_envs, slot_threads, slots, slot_bytes)
+    const bool vec = side % 4 == 0;
+    if (a.dead_rule == CGL_DEAD_DECAY) { if (vec) CGL_BYTES(true, CGL_DEAD_DECAY); else CGL_BYTES(false, CGL_DEAD_DECAY); }
+    else if (a.dead_rule == CGL_DEAD_SAT) { if (vec) CGL_BYTES(true, CGL_DEAD_SAT); else CGL_BYTES(false, CGL_DEAD_SAT); }
+    else { if (vec) CGL_BYTES(true, CGL_DEAD_ZERO); else CGL_BYTES(false, CGL_DEAD_ZERO); }
+#undef CGL_BYTES
     CGL_LAUNCH_CHECK();
     return 0;
 }
